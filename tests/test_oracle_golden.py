@@ -1,0 +1,157 @@
+"""CPU: pin oracle/maest_oracle.py against outputs of the unmodified reference (tests/golden/*.npz).
+
+Tolerances: the reference ran in fp32 on CPU; the oracle is evaluated in float64 (and fp32), so the
+gap is the reference's own fp32 rounding (~1e-6 relative).
+"""
+import numpy as np
+import pytest
+import torch
+
+from maest_b200 import synth
+from oracle import maest_oracle as O
+
+
+def rel(a, b):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30)
+
+
+def maxabs(a, b):
+    return float(np.max(np.abs(np.asarray(a, np.float64) - np.asarray(b, np.float64))))
+
+
+@pytest.fixture(scope="module")
+def sd10():
+    return synth.synth_state_dict(62, 400, seed=0)
+
+
+def test_filterbank_structure():
+    fb = O.mel_filterbank()
+    assert fb.shape == (257, 96)
+    assert float(fb[0].abs().max()) == 0.0 and float(fb[256].abs().max()) == 0.0
+    nnz = (fb > 0).sum().item()
+    assert nnz == 502                                     # SURVEY.md §9 [probed on torchaudio]
+    assert (fb > 0).sum(0).max().item() == 15
+
+
+def test_logmel_vs_reference(golden):
+    g = golden["c2"]
+    x = synth.wave_a(2, 160000)
+    m64 = O.logmel(x, torch.float64).numpy()
+    assert m64.shape == (2, 96, 626)
+    assert maxabs(m64[0], g["mel0"]) < 2e-5
+    assert maxabs(m64[1][:, ::5], g["mel1_sub"]) < 2e-5
+    m32 = O.logmel(x, torch.float32).numpy()
+    assert maxabs(m32[0], g["mel0"]) < 5e-5
+    mb = O.logmel(synth.wave_b(160000), torch.float64).numpy()
+    assert maxabs(mb, g["mel_waveb"]) < 5e-5
+
+
+def test_tokens_and_blocks_vs_reference(golden, sd10):
+    g = golden["c2"]
+    rows = list(g["row_probe"])
+    x = synth.wave_a(2, 160000)
+    mel = O.logmel(x, torch.float64)
+    tok = O.patch_tokens(mel, sd10)
+    assert tok.shape == (2, 560, 768)
+    assert maxabs(tok[:, rows].numpy(), g["tokens_probe"]) < 1e-5
+    h = tok
+    for i in range(12):
+        h = O.block(h, sd10, i)
+        assert rel(h[:, rows].numpy(), g[f"block{i}_probe"]) < 5e-6, i
+
+
+def test_logits_and_embeddings_vs_reference(golden, sd10):
+    g = golden["c2"]
+    x = synth.wave_a(2, 160000)
+    lo, em = O.forward(x, sd10, 625, dtype=torch.float64)
+    assert rel(lo.numpy(), g["logits"]) < 5e-6
+    assert rel(em.numpy(), g["emb"]) < 5e-6
+    for k in (0, 6, 11):
+        none, e = O.forward(x, sd10, 625, transformer_block=k, dtype=torch.float64)
+        assert none is None and e.shape == (2, 2304)
+        assert rel(e.numpy(), g[f"emb_block{k}"]) < 5e-6
+    e = O.forward(x, sd10, 625, transformer_block=6, return_self_attention=True, dtype=torch.float64)[1]
+    assert rel(e.numpy(), g["emb_block6_selfattn"]) < 5e-6
+    lo32, _ = O.forward(x, sd10, 625, dtype=torch.float32)
+    assert rel(lo32.numpy(), g["logits"]) < 2e-5
+
+
+def test_input_rank_dispatch_vs_reference(golden, sd10):
+    g = golden["c2"]
+    lo, em = O.forward(synth.wave_a(1, 400000, seed=99)[0], sd10, 625, dtype=torch.float64)
+    assert lo.shape == (2, 400)
+    assert rel(lo.numpy(), g["logits_25s_1d"]) < 5e-6 and rel(em.numpy(), g["emb_25s_1d"]) < 5e-6
+    lo, em = O.forward(synth.wave_a(1, 48000, seed=98)[0], sd10, 625, dtype=torch.float64)
+    assert rel(lo.numpy(), g["logits_3s_1d"]) < 5e-6
+    lo, _ = O.forward(synth.wave_b(160000)[None], sd10, 625, dtype=torch.float64)
+    assert rel(lo.numpy(), g["logits_waveb"]) < 5e-6
+    gen = torch.Generator().manual_seed(5)
+    m2 = torch.rand(96, 1300, generator=gen)
+    m3 = torch.rand(2, 96, 625, generator=gen)
+    assert rel(O.forward(m2, sd10, 625, melspectrogram_input=True, dtype=torch.float64)[0].numpy(),
+               g["logits_mel2d"]) < 5e-6
+    assert rel(O.forward(m3, sd10, 625, dtype=torch.float64)[0].numpy(), g["logits_mel3d"]) < 5e-6
+    assert rel(O.forward(m3[:, None], sd10, 625, dtype=torch.float64)[0].numpy(), g["logits_mel4d"]) < 5e-6
+
+
+def test_separated_heads_vs_reference(golden, sd10):
+    g = golden["c2sep"]
+    lc, ld, ft = O.forward(synth.wave_a(2, 160000), sd10, 625, distilled_type="separated", dtype=torch.float64)
+    assert rel(lc.numpy(), g["logits_cls"]) < 5e-6
+    assert rel(ld.numpy(), g["logits_dist"]) < 5e-6
+    assert rel(ft.numpy(), g["feats"]) < 5e-6
+
+
+def test_config1_1d_vs_reference(golden, sd10):
+    g = golden["c1"]
+    lo, em = O.forward(synth.wave_a(1, 160000)[0], sd10, 625, dtype=torch.float64)
+    assert lo.shape == (1, 400)
+    assert rel(lo.numpy(), g["logits64"]) < 5e-7          # fp64 oracle vs .double() reference (its fb/window buffers stay fp32-derived)
+    assert rel(em.numpy(), g["emb64"]) < 5e-7
+    assert rel(lo.numpy(), g["logits"]) < 5e-6
+
+
+@pytest.mark.slow
+def test_config3_30s_vs_reference(golden):
+    g = golden["c3"]
+    sd = synth.synth_state_dict(187, 400, seed=0)
+    x = synth.wave_a(2, 480000)
+    lo, em = O.forward(x, sd, 1875, dtype=torch.float32)
+    assert lo.shape == (2, 400)
+    assert rel(lo.numpy(), g["logits"]) < 2e-5
+    assert rel(em.numpy(), g["emb"]) < 2e-5
+    assert maxabs(O.logmel(x[0], torch.float64).numpy()[:, ::9], g["mel0_sub"]) < 2e-5
+
+
+@pytest.mark.slow
+def test_config5_predict_labels_vs_reference(golden):
+    g = golden["c5"]
+    sd = synth.synth_state_dict(187, 519, seed=0)
+    xa = synth.wave_a(1, 95 * 16000, seed=77)[0]
+    act = O.predict_labels(xa, sd, 1875, dtype=torch.float32)
+    assert act.shape == (519,)
+    assert maxabs(act.numpy(), g["act_a"]) < 1e-5
+    e = O.forward(synth.wave_b(95 * 16000), sd, 1875, transformer_block=6, dtype=torch.float32)[1]
+    assert e.shape == (3, 2304)
+    assert rel(e.numpy(), g["emb6_b"]) < 2e-5
+
+
+@pytest.mark.slow
+def test_config4_training_step_vs_reference(golden):
+    g = golden["c4"]
+    sd = {k: v.clone().requires_grad_(True) for k, v in synth.synth_state_dict(187, 400, seed=0).items()}
+    x, y = synth.train_batch(2)
+    loss = O.training_loss(x, y, sd, rn_indices=torch.as_tensor(g["rn"]), lam=torch.as_tensor(g["lam"]),
+                           t_offset=int(g["toffset"]), keep_t=list(g["keep_t"]), dtype=torch.float32)
+    assert abs(loss.item() - float(g["loss"])) < 1e-5
+    loss.backward()
+    for k in ["cls_token", "time_new_pos_embed", "patch_embed.proj.bias", "blocks.0.attn.qkv.bias",
+              "blocks.5.mlp.fc1.bias", "norm.weight", "head.1.bias"]:
+        assert rel(sd[k].grad.numpy(), g["grad." + k]) < 2e-4, k
+    for k in ["patch_embed.proj.weight", "blocks.0.attn.qkv.weight", "blocks.11.mlp.fc2.weight"]:
+        gr = sd[k].grad
+        assert rel(gr.reshape(gr.shape[0], -1)[::37, ::29].numpy(), g["grad." + k + ".sub"]) < 2e-4, k
+        assert abs(gr.double().norm().item() / float(g["gnorm." + k]) - 1) < 1e-4
+    assert sd["head_dist.weight"].grad is None
