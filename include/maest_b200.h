@@ -1,0 +1,125 @@
+/* maest_b200.h — C ABI of libmaest_b200.so: the B200 (sm_100a) hot path of palonso/MAEST.
+ *
+ * The reference (pure Python) has no FFI layer; its boundary for this path is the Python API
+ * (get_maest / MAEST.forward / predict_labels / Module.training_step).  This header is the C boundary we
+ * introduce UNDER that API: every entry point names the reference code it replaces (file:line relative to
+ * the reference repo root).  INTEGRATION.md shows the ctypes binding a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (e.g. torch tensors); nothing is allocated,
+ *     freed or retained; kernels are enqueued on `stream` (a cudaStream_t passed as void*); no host sync.
+ *   - return 0 on success, negative on error; maest_last_error() returns a thread-local message.
+ *   - "op16" tensors are 16-bit GEMM operands: dtype MAEST_F16 or MAEST_BF16 (same tensor-core rate).
+ *   - row-major everywhere; [M, K] means M rows of K contiguous elements.
+ */
+#ifndef MAEST_B200_H_
+#define MAEST_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+enum { MAEST_F16 = 0, MAEST_BF16 = 1, MAEST_F32 = 2 };
+
+/* GEMM epilogues (maest_linear_fwd) */
+enum {
+  MAEST_EPI_STORE16 = 0, /* out16 = A W^T + bias                                   (qkv: models/maest.py:361)            */
+  MAEST_EPI_GELU16 = 1,  /* out16 = gelu_erf(A W^T + bias)                         (fc1+GELU: models/maest.py:203-204)   */
+  MAEST_EPI_RESID32 = 2, /* out32 = resid32 + A W^T + bias                         (proj/fc2 + residual: :376,:206,:418-419) */
+  MAEST_EPI_STORE32 = 3  /* out32 = A W^T + bias (+ addend table, + row remap)     (patch-embed + pos-embed: :250,:670-675) */
+};
+
+/* pooling modes (maest_pool_head_fwd) */
+enum { MAEST_HEAD_MEAN = 0, MAEST_HEAD_SEPARATED = 1 };
+
+/* Per-block weights for maest_encoder_fwd (state-dict names: blocks.<i>.*; models/maest.py:381-420). */
+typedef struct MaestBlockWeights {
+  const float* ln1_w; const float* ln1_b;      /* norm1.{weight,bias}        [768]                 */
+  const void* qkv_w;  const float* qkv_b;      /* attn.qkv.weight op16 [2304,768], bias fp32 [2304] */
+  const void* proj_w; const float* proj_b;     /* attn.proj.weight op16 [768,768], bias [768]      */
+  const float* ln2_w; const float* ln2_b;      /* norm2.*                                         */
+  const void* fc1_w;  const float* fc1_b;      /* mlp.fc1.weight op16 [3072,768], bias [3072]      */
+  const void* fc2_w;  const float* fc2_b;      /* mlp.fc2.weight op16 [768,3072], bias [768]       */
+} MaestBlockWeights;
+
+const char* maest_last_error(void);
+/* ABI version of this header (bumped on any signature change). */
+int32_t maest_abi_version(void);
+/* Select device, resolve the driver's tensor-map encoder, opt kernels into >48 KB dynamic smem, upload K1 tables.
+ * Must be called once per process per device before any other call. */
+int32_t maest_init(int32_t device);
+
+/* K1 — waveform -> normalised log-mel.  Replaces MelSpectrogram.forward, models/helpers/melspectrogram.py:47-60
+ * (torchaudio Spectrogram + MelScale + log10(1+1e4 x) + z-norm) and helpers/melspectrogram_extractor.py:15-48.
+ * wav fp32 [B, S] with row stride wav_stride (elements); mel fp32 [B, 96, T], T = 1 + S/256.  Requires S > 256. */
+int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, float* mel, void* stream);
+
+/* K2 — mel -> packed token buffer.  Replaces PatchEmbed.forward (models/maest.py:243-256) and the pre-block part
+ * of MAEST.forward_features (:645-800): + time/freq pos-embed, structured/unstructured patchout, flatten,
+ * CLS/DIST rows.
+ *   mel        [B, 96, T] of mel_dtype (MAEST_F32 or MAEST_F16)
+ *   w_pe       patch_embed.proj.weight viewed [768, 256] as op16; conv_bias fp32 [768]
+ *   freq_pe    freq_new_pos_embed viewed [768, Fp];  time_pe  time_new_pos_embed viewed [768, Wt]
+ *   cls_token, dist_token [768]; new_pos_embed [2, 768]
+ *   keep_ft    device int32 [P]: kept grid cells (f << 16 | t) in sequence order, or NULL = all Fp*Tp cells
+ *   t_offset   column offset into time_pe (0 in eval; random in training, :647-657)
+ *   tokens     fp32 [B, 2 + P, 768] (out)
+ *   workspace  >= maest_patch_workspace_bytes(B, P) bytes
+ * Returns -2 if Tp + t_offset exceeds Wt (the reference raises, :664-668). */
+size_t maest_patch_workspace_bytes(int32_t B, int32_t P);
+int32_t maest_patch_tokens_fwd(const void* mel, int32_t mel_dtype, int32_t B, int32_t T, const void* w_pe,
+                               int32_t op_dtype, const float* conv_bias, const float* freq_pe, int32_t Fp,
+                               const float* time_pe, int32_t Wt, const float* cls_token, const float* dist_token,
+                               const float* new_pos_embed, const int32_t* keep_ft, int32_t P, int32_t t_offset,
+                               float* tokens, void* workspace, size_t workspace_bytes, void* stream);
+
+/* LayerNorm over 768-wide rows, fp32 in -> op16 out (GEMM operand).  Replaces norm1/norm2, models/maest.py:395,405,418-419.
+ * mean/rstd (fp32 [rows]) are optional saves for the backward pass (may be NULL). */
+int32_t maest_layernorm_fwd(const float* x, const float* w, const float* b, void* y16, int32_t op_dtype, int32_t rows,
+                            float eps, float* mean, float* rstd, void* stream);
+
+/* out = epilogue(A[M,K] W[N,K]^T): tcgen05 GEMM, A and W op16 (K contiguous, lda / ldw elements).  Replaces the nn.Linear /
+ * Conv2d-as-GEMM calls listed at the MAEST_EPI_* enum.  Output row of GEMM row m:
+ * (m / rows_per_group) * group_stride + row_offset + m % rows_per_group  (rows_per_group = 0 -> identity).
+ * addend: optional fp32 [rows_per_group, N] table added in MAEST_EPI_STORE32.  N % 32 == 0, K % 8 == 0. */
+int32_t maest_linear_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, int32_t M,
+                         int32_t N, int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out,
+                         const float* resid, const float* addend, int32_t rows_per_group, int32_t group_stride,
+                         int32_t row_offset, void* stream);
+
+/* Fused multi-head attention, d_head 64.  Replaces Attention.forward lines models/maest.py:362-375.
+ * qkv op16 [B*N, 3*H*64] as written by the qkv linear (columns = [q|k|v][head][64]); out op16 [B*N, H*64].
+ * variant: 0 = P kept in TMEM (tcgen05.mma A-from-TMEM), 1 = P staged through shared memory. */
+int32_t maest_attention_fwd(const void* qkv, void* out, int32_t B, int32_t N, int32_t H, int32_t op_dtype,
+                            int32_t variant, void* stream);
+
+/* The 12-block encoder on the fp32 residual stream x [B*N, 768], in place.  Replaces Block.forward x n_blocks
+ * (models/maest.py:414-420, driven from :804-820).  If last_attn_only != 0 the last block writes attn(norm1(x))
+ * WITHOUT residual into x (return_self_attention, :415-416).  workspace >= maest_encoder_workspace_bytes(B*N). */
+size_t maest_encoder_workspace_bytes(int64_t rows);
+int32_t maest_encoder_fwd(float* x, int32_t B, int32_t N, const MaestBlockWeights* blocks, int32_t n_blocks,
+                          int32_t last_attn_only, int32_t op_dtype, int32_t attn_variant, void* workspace,
+                          size_t workspace_bytes, void* stream);
+
+/* Pooling + head.  Replaces models/maest.py:806-810 (final LN, only rows 0/1 are normalised) and :905-925.
+ * x fp32 [B, N, 768]; logits [B, C]; logits_dist [B, C] (MAEST_HEAD_SEPARATED only, else NULL); feats [B, 768].
+ * ln_cls / ln_dist: optional [B,768] saves of the normalised cls / dist rows (NULL in inference). */
+int32_t maest_pool_head_fwd(const float* x, int32_t B, int32_t N, const float* norm_w, const float* norm_b,
+                            const float* head_ln_w, const float* head_ln_b, const float* head_w, const float* head_b,
+                            const float* head_dist_w, const float* head_dist_b, int32_t C, int32_t mode,
+                            float* logits, float* logits_dist, float* feats, float* ln_cls, float* ln_dist,
+                            void* stream);
+
+/* Block-k embedding: emb[b] = cat(x[b,0], x[b,1], mean(x[b,2:], 0)), fp32 [B, 2304].  Replaces models/maest.py:825-829. */
+int32_t maest_block_embedding_fwd(const float* x, int32_t B, int32_t N, float* emb, void* stream);
+
+/* fp32 -> op16 cast (weight staging). */
+int32_t maest_cast_to16(const float* src, void* dst, int64_t n, int32_t op_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MAEST_B200_H_ */

@@ -1,0 +1,287 @@
+// Flash-style attention forward for sm_100a (tcgen05 + TMEM + TMA), d_head = 64, no N x N matrix in HBM.
+//
+// Replaces models/maest.py:362-375 (reshape/permute, q@k^T*scale, softmax, attn@v, transpose) — the
+// reference materialises [B,12,N,N] several times per block.
+//
+// Input is the packed qkv activation [B*N, 3*768] (16-bit) exactly as the qkv GEMM writes it; q/k/v
+// tiles of head h are fetched by TMA as 64-column boxes at column offsets {0,768,1536} + 64 h, so no
+// head-major re-layout pass exists.  Output o[B*N, 768] (16-bit), column block 64 h.
+//
+// CTA = one 128-query tile of one (clip, head); 2 CTAs co-reside per SM (256 TMEM columns, <=112 KB smem
+// each) so one CTA's softmax overlaps the other's MMAs.
+//   warps 0..3  softmax: thread = one query row (tcgen05.ld 32x32b: TMEM lane == row), online softmax in
+//               fp32 with exp2 and lazy rescaling of the O accumulator, P written as 16-bit
+//   warp 4      TMA producer (Q once, K/V double-buffered) + TMEM allocator
+//   warp 5      MMA issuer: S = Q K^T (128x128x64), O += P V (128x64x128); V is consumed in its natural
+//               [key][d] layout as an MN-major B operand
+// P_IN_TMEM: P is stored back to TMEM (tcgen05.st) and fed as the A operand from TMEM (no smem round trip).
+#pragma once
+#include "common.cuh"
+
+namespace mb {
+
+constexpr int ATT_BQ = 128;
+constexpr int ATT_BKV = 128;
+constexpr int ATT_D = 64;
+constexpr int ATT_THREADS = 192;
+constexpr int ATT_TILE_BYTES = 128 * 64 * 2;  // 16 KB: any [128 x 64] 16-bit tile
+constexpr int ATT_KV_STAGES = 2;
+
+template <bool P_IN_TMEM>
+__host__ __device__ constexpr int att_smem_bytes() {
+  return ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES + (P_IN_TMEM ? 0 : 2)) + 128;
+}
+
+struct AttnParams {
+  int B, N;         // clips, tokens per clip (rows of clip b are [b*N, (b+1)*N))
+  int H;            // heads
+  int ld_qkv;       // 3*H*64
+  int ld_out;       // H*64
+  void* out;        // [B*N, H*64] 16-bit
+  float scale_log2; // d^-0.5 * log2(e)
+};
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+template <int DT, bool P_IN_TMEM>
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using O16 = Op16<DT>;
+  uint8_t* sQ = smem;
+  uint8_t* sK = smem + ATT_TILE_BYTES;                              // [stages]
+  uint8_t* sV = smem + ATT_TILE_BYTES * (1 + ATT_KV_STAGES);        // [stages]
+  uint8_t* sP = smem + ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES);    // SS mode only: two [128 x 64] halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + att_smem_bytes<P_IN_TMEM>() - 128);
+  uint64_t* q_full = bars;            // 1
+  uint64_t* kv_full = bars + 1;       // [2]
+  uint64_t* kv_empty = bars + 3;      // [2]
+  uint64_t* s_full = bars + 5;        // 1
+  uint64_t* p_full = bars + 6;        // 1 (count 128)
+  uint64_t* o_done = bars + 7;        // 1
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int q0 = blockIdx.x * ATT_BQ;
+  const int h = blockIdx.y;
+  const int b = blockIdx.z;
+  const int row_base = b * p.N;
+  const int nkv = (p.N + ATT_BKV - 1) / ATT_BKV;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("attention: dynamic smem base not 1024-aligned\n");
+    __trap();
+  }
+  if (warp == 5 && lane == 0) {
+    mbar_init(q_full, 1);
+    for (int i = 0; i < ATT_KV_STAGES; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(o_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) tma_prefetch_desc(&tmap_qkv);
+    tmem_alloc<256>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base;          // 128 fp32 columns
+  const uint32_t tO = tmem_base + 128;    // 64 fp32 columns
+  const uint32_t tP = tmem_base + 192;    // 64 columns of packed 16-bit pairs (TS mode)
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, ATT_TILE_BYTES);
+      tma_load_2d(sQ, &tmap_qkv, q_full, h * ATT_D, row_base + q0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(&kv_empty[stage], phase ^ 1);
+        mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
+        const int r = row_base + j * ATT_BKV;
+        tma_load_2d(sK + stage * ATT_TILE_BYTES, &tmap_qkv, &kv_full[stage], p.H * ATT_D + h * ATT_D, r);
+        tma_load_2d(sV + stage * ATT_TILE_BYTES, &tmap_qkv, &kv_full[stage], 2 * p.H * ATT_D + h * ATT_D, r);
+        if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);
+      constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);  // B = V, MN-major
+      const uint64_t qdesc = make_sdesc(smem_u32(sQ), 16, 1024);
+      auto issue_qk = [&](int stage) {
+        const uint64_t kdesc = make_sdesc(smem_u32(sK + stage * ATT_TILE_BYTES), 16, 1024);
+#pragma unroll
+        for (int k = 0; k < ATT_D / 16; ++k)
+          mma_ss(tS, qdesc + uint64_t(2 * k), kdesc + uint64_t(2 * k), idesc_qk, k ? 1u : 0u);
+        tc_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      mbar_wait(&kv_full[0], 0);
+      tc_fence_after();
+      issue_qk(0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int j = 0; j < nkv; ++j) {
+        mbar_wait(p_full, j & 1);   // P_j written, S_j consumed
+        tc_fence_after();
+        int nstage = stage + 1;
+        uint32_t nphase = phase;
+        if (nstage == ATT_KV_STAGES) { nstage = 0; nphase ^= 1; }
+        if (j + 1 < nkv) {
+          mbar_wait(&kv_full[nstage], nphase);
+          tc_fence_after();
+          issue_qk(nstage);
+        }
+        // O (+)= P_j V_j : 8 K-steps of 16 keys
+        const uint32_t vbase = smem_u32(sV + stage * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < ATT_BKV / 16; ++k) {
+          const uint64_t vdesc = make_sdesc(vbase + uint32_t(k * 16 * 128), 8192, 1024);
+          if constexpr (P_IN_TMEM) {
+            mma_ts(tO, tP + uint32_t(8 * k), vdesc, idesc_pv, (j | k) ? 1u : 0u);
+          } else {
+            const uint64_t pdesc = make_sdesc(smem_u32(sP + (k >> 2) * ATT_TILE_BYTES), 16, 1024) + uint64_t(2 * (k & 3));
+            mma_ss(tO, pdesc, vdesc, idesc_pv, (j | k) ? 1u : 0u);
+          }
+        }
+        tc_commit(&kv_empty[stage]);
+        tc_commit(o_done);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    // ---------------- softmax warps: thread <-> query row (TMEM lane) ----------------
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    float m_run = -INFINITY;  // running max of s * scale_log2
+    float l_run = 0.f;
+    const float sc = p.scale_log2;
+    for (int j = 0; j < nkv; ++j) {
+      const int kv0 = j * ATT_BKV;
+      const int valid = p.N - kv0;  // keys [0, valid) of this tile are real (>=128 when not the last tile)
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      // pass 1: row max
+      float mt = -INFINITY;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + uint32_t(c * 32), v);
+        tc_wait_ld();
+        if (valid >= (c + 1) * 32) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (c * 32 + i < valid) mt = fmaxf(mt, __uint_as_float(v[i]));
+        }
+      }
+      const float mt_sc = mt * sc;
+      if (j > 0) {
+        // PV_{j-1} must be complete before O is corrected or P is overwritten
+        mbar_wait(o_done, (j - 1) & 1);
+        tc_fence_after();
+        const bool need = mt_sc > m_run + 8.0f;   // lazy rescale: p stays <= 2^8 against a stale max
+        if (__any_sync(0xffffffffu, need)) {
+          float f = 1.0f;
+          if (need) {
+            f = ex2_approx(m_run - mt_sc);
+            m_run = mt_sc;
+            l_run *= f;
+          }
+#pragma unroll 1
+          for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + uint32_t(c * 32), v);
+            tc_wait_ld();
+#pragma unroll
+            for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * f);
+            tmem_st32(tO + lane_off + uint32_t(c * 32), v);
+          }
+          tc_wait_st();
+        }
+      } else {
+        m_run = mt_sc;
+      }
+      // pass 2: p = exp2(s*sc - m), row sum, P -> 16-bit
+      const float neg_m = -m_run;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tS + lane_off + uint32_t(c * 32), v);
+        tc_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));
+          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
+          if (c * 32 + i >= valid) p0 = 0.f;
+          if (c * 32 + i + 1 >= valid) p1 = 0.f;
+          l_run += p0 + p1;
+          pk[i >> 1] = O16::pack(p0, p1);
+        }
+        if constexpr (P_IN_TMEM) {
+          tmem_st16(tP + lane_off + uint32_t(c * 16), pk);
+        } else {
+          // K-major SWIZZLE_128B tile [128 rows x 64 keys]: 16-byte chunk index XOR (row & 7)
+          uint8_t* base = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = ((c & 1) * 4 + q4) ^ (row & 7);
+            *reinterpret_cast<uint4*>(base + chunk * 16) =
+                make_uint4(pk[4 * q4], pk[4 * q4 + 1], pk[4 * q4 + 2], pk[4 * q4 + 3]);
+          }
+        }
+      }
+      if constexpr (P_IN_TMEM) tc_wait_st();
+      else fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    // ---------------- epilogue: O / l -> 16-bit ----------------
+    mbar_wait(o_done, (nkv - 1) & 1);
+    tc_fence_after();
+    const float inv_l = 1.0f / l_run;
+    const int qrow = q0 + row;
+    typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.out) + long(row_base + qrow) * p.ld_out + h * ATT_D;
+#pragma unroll 1
+    for (int c = 0; c < 2; ++c) {
+      uint32_t v[32];
+      tmem_ld32(tO + lane_off + uint32_t(c * 32), v);
+      tc_wait_ld();
+      if (qrow < p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8) {
+          st_global_v4(dst + c * 32 + i,
+                       O16::pack(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
+                       O16::pack(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
+                       O16::pack(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
+                       O16::pack(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<256>(tmem_base);
+  }
+}
+
+}  // namespace mb

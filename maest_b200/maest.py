@@ -1,0 +1,521 @@
+"""`get_maest()` / `MAEST` — the reference's model API (models/maest.py:423-939, :1441-1569) on the B200 kernels.
+
+The module keeps the reference's parameter names and shapes (state-dict contract), its
+`forward` input-rank dispatch, exceptions and return conventions, so `load_state_dict` from a reference
+checkpoint, Lightning, AdamW and the SWA deep-copy all work unchanged.  The arithmetic is NOT done by these
+`nn.Module`s: `nn.Linear` / `nn.LayerNorm` / `nn.Conv2d` are used as parameter containers only and the
+forward pass calls libmaest_b200.so (ops.py).  No CPU path exists; CPU tensors raise.
+"""
+from __future__ import annotations
+
+import json
+import logging
+import os
+import warnings
+from typing import Optional, Tuple
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+
+_logger = logging.getLogger("MAEST")
+
+EMBED, DEPTH, HEADS, PATCH = 768, 12, 12, 16
+
+with open(os.path.join(os.path.dirname(__file__), "data", "discogs_labels.json"), encoding="utf-8") as _f:
+    _LABELS = json.load(_f)
+discogs_400labels = _LABELS["discogs_400labels"]
+discogs_519labels = _LABELS["discogs_519labels"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# Sacred ingredient (models/maest.py:1441-1464).  Real sacred is used when installed; otherwise a minimal
+# stand-in that injects the ingredient defaults into captured functions, as sacred would.
+# ---------------------------------------------------------------------------------------------------
+MAEST_DEFAULT_CONF = dict(
+    arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=400, in_channels=1, stride_f=10, stride_t=10,
+    input_f=96, input_t=998, u_patchout=0, s_patchout_t=0, s_patchout_f=0, s_patchout_f_indices=(),
+    s_patchout_f_interleaved=0, s_patchout_t_indices=(), s_patchout_t_interleaved=0, distilled_type="mean",
+    checkpoint=None, checkpoint_swa_weigts=True, checkpoint_discard_head=False,
+)
+
+
+class _MiniIngredient:
+    """Captured functions called OUTSIDE a run see only their own defaults (as with sacred: tests/test_maest.py:10
+    calls get_maest(arch=..., pretrained=False) and gets the per-arch input_t); inside `with ing.run(**updates):`
+    missing arguments are filled from the ingredient config, which is what `Module.__init__` relies on
+    (models/module.py:63 calls get_maest() with no arguments)."""
+
+    def __init__(self, name):
+        self.path = name
+        self.cfg = {}
+        self.active = False
+
+    def run(self, **updates):
+        import contextlib
+
+        @contextlib.contextmanager
+        def _ctx():
+            old_cfg, old_active = dict(self.cfg), self.active
+            self.cfg.update(updates)
+            self.active = True
+            try:
+                yield self
+            finally:
+                self.cfg, self.active = old_cfg, old_active
+
+        return _ctx()
+
+    def config(self, f):
+        return f
+
+    def add_config(self, d=None, **kw):
+        self.cfg.update(d or {}, **kw)
+
+    def capture(self, f=None, prefix=None):
+        import functools
+        import inspect
+
+        def deco(fn):
+            sig = inspect.signature(fn)
+
+            @functools.wraps(fn)
+            def wrapper(*a, **k):
+                bound = sig.bind_partial(*a, **k)
+                for name, prm in sig.parameters.items():
+                    required = prm.default is inspect.Parameter.empty
+                    if name not in bound.arguments and name in self.cfg and (self.active or required):
+                        k[name] = self.cfg[name]
+                return fn(*a, **k)
+
+            return wrapper
+
+        return deco(f) if f is not None else deco
+
+
+try:  # pragma: no cover - sacred is not installed in the build image
+    from sacred import Ingredient as _SacredIngredient
+
+    maest_ing = _SacredIngredient("maest")
+    maest_ing.add_config(MAEST_DEFAULT_CONF)
+except Exception:  # noqa: BLE001
+    maest_ing = _MiniIngredient("maest")
+    maest_ing.add_config(MAEST_DEFAULT_CONF)
+
+
+# ---------------------------------------------------------------------------------------------------
+# parameter containers mirroring the reference's module tree (names == state-dict keys)
+# ---------------------------------------------------------------------------------------------------
+class _NoForward(nn.Module):
+    def forward(self, *a, **k):  # pragma: no cover
+        raise RuntimeError("parameter container: the forward pass runs in libmaest_b200.so via MAEST.forward")
+
+
+class PatchEmbed(_NoForward):
+    """models/maest.py:214-256 (Conv2d(1,768,16,stride 10), flatten=False)."""
+
+    def __init__(self, img_size, patch_size=16, stride=(10, 10), in_chans=1, embed_dim=EMBED):
+        super().__init__()
+        self.img_size = tuple(img_size)
+        self.patch_size = (patch_size, patch_size)
+        self.stride = tuple(stride)
+        self.grid_size = (img_size[0] // stride[0], img_size[1] // stride[1])   # :234
+        self.num_patches = self.grid_size[0] * self.grid_size[1]
+        self.embed_dim = embed_dim
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch_size, stride=stride)
+
+
+class Attention(_NoForward):
+    def __init__(self, dim=EMBED, num_heads=HEADS):
+        super().__init__()
+        self.num_heads = num_heads
+        self.scale = (dim // num_heads) ** -0.5
+        self.qkv = nn.Linear(dim, dim * 3, bias=True)
+        self.proj = nn.Linear(dim, dim)
+
+
+class Mlp(_NoForward):
+    def __init__(self, dim=EMBED, hidden=4 * EMBED):
+        super().__init__()
+        self.fc1 = nn.Linear(dim, hidden)
+        self.fc2 = nn.Linear(hidden, dim)
+
+
+class Block(_NoForward):
+    def __init__(self, dim=EMBED, num_heads=HEADS):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=1e-6)
+        self.attn = Attention(dim, num_heads)
+        self.norm2 = nn.LayerNorm(dim, eps=1e-6)
+        self.mlp = Mlp(dim, 4 * dim)
+
+
+class _Buf(nn.Module):
+    def __init__(self, name, t):
+        super().__init__()
+        self.register_buffer(name, t)
+
+
+def _slaney_fb() -> torch.Tensor:
+    """[257, 96] Slaney-scale / Slaney-normalised triangular filterbank (informational buffer; same formula as
+    csrc/logmel_tables.h, which is what the kernel actually uses)."""
+    import math
+    f_sp, min_log_hz, logstep = 200.0 / 3, 1000.0, math.log(6.4) / 27.0
+    min_log_mel = min_log_hz / f_sp
+    m_max = min_log_mel + math.log(8000.0 / min_log_hz) / logstep
+    m = torch.linspace(0.0, m_max, 98, dtype=torch.float64)
+    f = torch.where(m >= min_log_mel, min_log_hz * torch.exp(logstep * (m - min_log_mel)), f_sp * m)
+    bins = torch.linspace(0, 8000, 257, dtype=torch.float64)
+    sl = f[None, :] - bins[:, None]
+    fd = f[1:] - f[:-1]
+    fb = torch.clamp(torch.minimum(-sl[:, :-2] / fd[:-1], sl[:, 2:] / fd[1:]), min=0.0)
+    return (fb * (2.0 / (f[2:] - f[:-2]))[None, :]).float()
+
+
+class MelSpectrogram(nn.Module):
+    """models/helpers/melspectrogram.py:13-60 on the fused K1 kernel.  Keeps the reference's two buffers
+    (`spec.window`, `mel_scale.fb`) so reference state dicts load strictly; the kernel uses its own
+    double-precision-derived tables (csrc/logmel_tables.h)."""
+
+    sr, win_len, hop_len, power, n_mel = 16000, 512, 256, 2, 96
+    norm, mel_scale_type = "slaney", "slaney"
+    norm_mean, norm_std = 2.06755686098554, 1.268292820667291
+
+    def __init__(self):
+        super().__init__()
+        self.spec = _Buf("window", torch.hann_window(512, periodic=True))
+        self.mel_scale = _Buf("fb", _slaney_fb())
+
+    def forward(self, waveform: torch.Tensor) -> torch.Tensor:
+        return ops.logmel(waveform)
+
+
+def trunc_normal_(t, std=0.02):
+    return nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2.0, b=2.0)   # vit_helpers.py:110-166 semantics
+
+
+class MAEST(nn.Module):
+    def __init__(self, u_patchout=0, s_patchout_t=0, s_patchout_f=0, s_patchout_f_indices=(),
+                 s_patchout_f_interleaved=0, s_patchout_t_indices=(), s_patchout_t_interleaved=0,
+                 img_size=(96, 1875), patch_size=16, stride=(10, 10), in_chans=1, num_classes=400,
+                 embed_dim=EMBED, depth=DEPTH, num_heads=HEADS, distilled=True, distilled_type="mean",
+                 op_dtype="fp16", attn_variant=0):
+        super().__init__()
+        if embed_dim != EMBED or num_heads != HEADS or patch_size != PATCH or in_chans != 1 or not distilled:
+            raise NotImplementedError("the B200 path is specialised to ViT-Base/16, 12 heads, mono, distilled (all shipped MAEST configs)")
+        if tuple(stride) != (10, 10):
+            raise NotImplementedError("the B200 patch kernels are specialised to stride (10, 10)")
+        self.num_classes = num_classes
+        self.u_patchout = u_patchout
+        self.img_size = tuple(img_size)
+        self.s_patchout_t = s_patchout_t
+        self.s_patchout_f = s_patchout_f
+        self.s_patchout_f_indices = s_patchout_f_indices
+        self.s_patchout_f_interleaved = s_patchout_f_interleaved
+        self.s_patchout_t_indices = s_patchout_t_indices
+        self.s_patchout_t_interleaved = s_patchout_t_interleaved
+        self.num_features = self.embed_dim = embed_dim
+        self.num_tokens = 2
+        self.distilled_type = distilled_type
+        self.op_dtype = op_dtype          # 16-bit GEMM operand type: "fp16" (default, tighter parity) or "bf16"
+        self.attn_variant = attn_variant
+        if num_classes == 400:
+            self.labels = discogs_400labels
+        elif num_classes == 519:
+            self.labels = discogs_519labels
+
+        self.patch_embed = PatchEmbed(img_size, patch_size, stride, in_chans, embed_dim)
+        self.num_patches = self.patch_embed.num_patches
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.dist_token = nn.Parameter(torch.zeros(1, 1, embed_dim))
+        self.new_pos_embed = nn.Parameter(torch.zeros(1, 2, embed_dim))
+        self.freq_new_pos_embed = nn.Parameter(torch.zeros(1, embed_dim, self.patch_embed.grid_size[0], 1))
+        self.time_new_pos_embed = nn.Parameter(torch.zeros(1, embed_dim, 1, self.patch_embed.grid_size[1]))
+        self.blocks = nn.Sequential(*[Block(embed_dim, num_heads) for _ in range(depth)])
+        self.norm = nn.LayerNorm(embed_dim, eps=1e-6)
+        self.head = nn.Sequential(nn.LayerNorm(embed_dim), nn.Linear(embed_dim, num_classes))
+        self.head_dist = nn.Linear(embed_dim, num_classes)
+        self.init_weights()
+        self.melspectrogram = MelSpectrogram()
+        self._w16 = {}          # op16 copies of GEMM weights, keyed by (name, dtype); refreshed on version change
+        self._ws = None         # encoder workspace
+        self._block_table = None
+
+    # -- init / bookkeeping ------------------------------------------------------------------------
+    def init_weights(self):
+        """models/maest.py:588-600, :942-976 (trunc_normal std .02 linears, zero biases, unit LayerNorm)."""
+        for t in (self.new_pos_embed, self.freq_new_pos_embed, self.time_new_pos_embed, self.dist_token, self.cls_token):
+            trunc_normal_(t, std=0.02)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                trunc_normal_(m.weight, std=0.02)
+                nn.init.zeros_(m.bias)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.zeros_(m.bias)
+                nn.init.ones_(m.weight)
+
+    @torch.jit.ignore
+    def no_weight_decay(self):
+        return {"new_pos_embed", "freq_new_pos_embed", "time_new_pos_embed", "cls_token", "dist_token"}
+
+    def get_classifier(self):
+        return self.head, self.head_dist
+
+    def __deepcopy__(self, memo):
+        # caches hold raw device pointers: never share them with a copy (helpers/swa_callback.py:43-44 deep-copies the net)
+        import copy
+        cls = self.__class__
+        new = cls.__new__(cls)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            if k in ("_w16", "_ws", "_block_table"):
+                continue
+            setattr(new, k, copy.deepcopy(v, memo))
+        new._w16, new._ws, new._block_table = {}, None, None
+        return new
+
+    def _op_torch_dtype(self):
+        return torch.float16 if ops.op_dtype_code(self.op_dtype) == ops.F16 else torch.bfloat16
+
+    def _weight16(self, name: str, p: torch.Tensor) -> torch.Tensor:
+        """16-bit operand copy of an fp32 master weight, re-staged when the parameter changes."""
+        key = (name, self._op_torch_dtype())
+        ver = (p._version, p.data_ptr(), p.device)
+        hit = self._w16.get(key)
+        if hit is None or hit[0] != ver:
+            w = p.detach().reshape(p.shape[0], -1)
+            hit = (ver, ops.cast16(w, self.op_dtype))
+            self._w16[key] = hit
+            self._block_table = None
+        return hit[1]
+
+    def _f32(self, p: torch.Tensor) -> torch.Tensor:
+        t = p.detach()
+        if t.dtype != torch.float32:
+            t = t.float()
+        return t.contiguous()
+
+    def _blocks_ctypes(self):
+        """MaestBlockWeights[depth] with current device pointers (rebuilt if any parameter was re-staged/moved)."""
+        sig = []
+        rows = []
+        keep = []
+        for i, blk in enumerate(self.blocks):
+            w16 = [self._weight16(f"blocks.{i}.{n}", p) for n, p in (("qkv", blk.attn.qkv.weight), ("proj", blk.attn.proj.weight),
+                                                                     ("fc1", blk.mlp.fc1.weight), ("fc2", blk.mlp.fc2.weight))]
+            f32 = [self._f32(p) for p in (blk.norm1.weight, blk.norm1.bias, blk.attn.qkv.bias, blk.attn.proj.bias,
+                                          blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.bias, blk.mlp.fc2.bias)]
+            keep += w16 + f32
+            rows.append(_lib.MaestBlockWeights(
+                ln1_w=f32[0].data_ptr(), ln1_b=f32[1].data_ptr(), qkv_w=w16[0].data_ptr(), qkv_b=f32[2].data_ptr(),
+                proj_w=w16[1].data_ptr(), proj_b=f32[3].data_ptr(), ln2_w=f32[4].data_ptr(), ln2_b=f32[5].data_ptr(),
+                fc1_w=w16[2].data_ptr(), fc1_b=f32[6].data_ptr(), fc2_w=w16[3].data_ptr(), fc2_b=f32[7].data_ptr()))
+            sig += [t.data_ptr() for t in w16 + f32]
+        sig = tuple(sig)
+        if self._block_table is None or self._block_table[0] != sig:
+            arr = (_lib.MaestBlockWeights * len(rows))(*rows)
+            self._block_table = (sig, arr, keep)
+        return self._block_table[1]
+
+    # -- hot path ---------------------------------------------------------------------------------
+    def _draw_patchout(self, Fp: int, Tp: int):
+        """Host RNG draws in the reference's call order (models/maest.py:647-650, :684-686, :696-698, :703-766, :773-777)."""
+        t_offset = 0
+        Wt = self.time_new_pos_embed.shape[-1]
+        if Tp > Wt:
+            raise Exception(
+                f"the patches shape:{(EMBED, Fp, Tp)} are larger than the expected time encodings "
+                f"{tuple(self.time_new_pos_embed.shape)}, please reduce the input duration.")
+        if self.training:
+            t_offset = int(torch.randint(1 + Wt - Tp, (1,)).item())
+        keep_t = keep_f = None
+        if self.training and self.s_patchout_t:
+            keep_t = torch.randperm(Tp)[: Tp - self.s_patchout_t].sort().values
+        if self.training and self.s_patchout_f:
+            keep_f = torch.randperm(Fp)[: Fp - self.s_patchout_f].sort().values
+
+        def _sub(cur, n, idx):
+            base = torch.arange(n) if cur is None else cur
+            return base[idx]
+
+        if self.s_patchout_f_indices:
+            n = Fp if keep_f is None else len(keep_f)
+            kept = torch.arange(n)
+            for i in self.s_patchout_f_indices:
+                kept = kept[kept != int(i)]
+            keep_f = _sub(keep_f, Fp, kept)
+        if self.s_patchout_f_interleaved:
+            n = Fp if keep_f is None else len(keep_f)
+            keep_f = _sub(keep_f, Fp, torch.arange(0, n, self.s_patchout_f_interleaved))
+        if self.s_patchout_t_indices:
+            n = Tp if keep_t is None else len(keep_t)
+            kept = torch.arange(n)
+            for i in self.s_patchout_t_indices:
+                kept = kept[kept != int(i)]
+            keep_t = _sub(keep_t, Tp, kept)
+        if self.s_patchout_t_interleaved:
+            n = Tp if keep_t is None else len(keep_t)
+            keep_t = _sub(keep_t, Tp, torch.arange(0, n, self.s_patchout_t_interleaved))
+        keep_seq = None
+        if self.training and self.u_patchout:
+            seq_len = (Fp if keep_f is None else len(keep_f)) * (Tp if keep_t is None else len(keep_t))
+            keep_seq = torch.randperm(seq_len)[: seq_len - self.u_patchout].sort().values
+        return t_offset, keep_f, keep_t, keep_seq
+
+    def tokens_from_mel(self, mel: torch.Tensor) -> torch.Tensor:
+        """[B,96,T] mel -> packed fp32 token buffer [B, N, 768] entering blocks[0] (forward_features up to :800)."""
+        B, Fm, T = mel.shape
+        Fp, Tp = (Fm - PATCH) // 10 + 1, (T - PATCH) // 10 + 1
+        t_offset, keep_f, keep_t, keep_seq = self._draw_patchout(Fp, Tp)
+        keep_ft = ops.keep_ft_tensor(keep_f, keep_t, Fp, Tp, keep_seq, mel.device)
+        if mel.dtype not in (torch.float32, torch.float16):
+            mel = mel.float()
+        return ops.patch_tokens(
+            mel.contiguous(), self._weight16("patch_embed.proj", self.patch_embed.proj.weight),
+            self._f32(self.patch_embed.proj.bias), self._f32(self.freq_new_pos_embed).reshape(EMBED, -1),
+            self._f32(self.time_new_pos_embed).reshape(EMBED, -1), self._f32(self.cls_token).reshape(-1),
+            self._f32(self.dist_token).reshape(-1), self._f32(self.new_pos_embed).reshape(2, EMBED),
+            keep_ft=keep_ft, t_offset=t_offset)
+
+    def forward_features(self, x, transformer_block=-1, return_self_attention=False):
+        """x: [B,1,96,T] or [B,96,T] mel.  models/maest.py:634-829."""
+        if x.dim() == 4:
+            x = x[:, 0]
+        tok = self.tokens_from_mel(x)
+        B, N, _ = tok.shape
+        xs = tok.view(B * N, EMBED)
+        table = self._blocks_ctypes()
+        depth = len(self.blocks)
+        if transformer_block == -1:
+            ops.encoder(xs, B, N, table, depth, False, self.op_dtype, self.attn_variant, self._workspace(B * N, xs.device))
+            return tok                      # un-normalised stream; pooling + final LN happen in pool_head
+        # the reference loops over all blocks and breaks at i == transformer_block (:812-820): an index that
+        # never matches (negative other than -1, or >= depth) runs every block and ignores return_self_attention
+        hit = 0 <= int(transformer_block) < depth
+        nb = int(transformer_block) + 1 if hit else depth
+        attn_only = bool(return_self_attention) and hit
+        ops.encoder(xs, B, N, table, nb, attn_only, self.op_dtype, self.attn_variant, self._workspace(B * N, xs.device))
+        return ops.block_embedding(tok, B, N)
+
+    def _workspace(self, rows: int, device):
+        need = _lib.load().maest_encoder_workspace_bytes(rows)
+        if self._ws is None or self._ws.numel() < need or self._ws.device != device:
+            self._ws = torch.empty(need, device=device, dtype=torch.uint8)
+        return self._ws
+
+    def _device(self):
+        return self.cls_token.device
+
+    def forward(self, x, transformer_block: int = -1, return_self_attention: bool = False,
+                melspectrogram_input: bool = False) -> Tuple[Optional[torch.Tensor], torch.Tensor]:
+        """Same contract as the reference's MAEST.forward (models/maest.py:831-933)."""
+        assert isinstance(x, torch.Tensor), "Input must be a torch.Tensor"
+        assert x.nelement() > 0, "Input tensor must not be empty"
+        dev = self._device()
+        if dev.type != "cuda":
+            raise RuntimeError("maest_b200: move the model to a CUDA device (B200, sm_100a); there is no CPU path")
+        caller_x = x
+        if x.device != dev:
+            x = x.to(dev, non_blocking=True)
+        img_t = self.img_size[1]
+
+        if x.dim() == 1:
+            assert melspectrogram_input is False, "Input is 1D, but melspectrogram_input is True. This is not supported."
+            m = self.melspectrogram(x)                               # [96, T]
+            if m.shape[1] >= img_t:
+                trim = m.shape[1] % img_t
+                if trim:
+                    m = m[:, :-trim]
+                mel = m.reshape(96, -1, img_t).transpose(0, 1).contiguous()   # :873-875
+            else:
+                mel = m[None]
+        elif x.dim() == 2 and melspectrogram_input:
+            trim = x.shape[1] % img_t
+            if trim:
+                x = x[:, :-trim]
+            mel = x.reshape(self.img_size[0], -1, img_t).transpose(0, 1).contiguous()
+        elif x.dim() == 2:
+            mel = self.melspectrogram(x)                             # no trimming (:890-892)
+        elif x.dim() == 3:
+            mel = x.detach().view(x.shape[0], x.shape[1], x.shape[2])
+            caller_x.unsqueeze_(1)                                   # the reference mutates the caller's tensor (:895)
+        elif x.dim() == 4:
+            mel = x[:, 0]
+        else:
+            raise AssertionError(f"unsupported input rank {x.dim()}")
+
+        if mel.shape[0] == 0:
+            # 2-D mel shorter than img_size[1] -> empty batch, as in the reference
+            C_ = self.num_classes
+            if transformer_block != -1:
+                return None, torch.empty((0, 3 * EMBED), device=dev)
+            return torch.empty((0, C_), device=dev), torch.empty((0, EMBED), device=dev)
+
+        out = self.forward_features(mel, transformer_block=transformer_block, return_self_attention=return_self_attention)
+        if transformer_block != -1:
+            return None, out
+        B, N, _ = out.shape
+        sep = self.distilled_type == "separated"
+        logits, logits_dist, feats = ops.pool_head(
+            out, B, N, self._f32(self.norm.weight), self._f32(self.norm.bias), self._f32(self.head[0].weight),
+            self._f32(self.head[0].bias), self._f32(self.head[1].weight), self._f32(self.head[1].bias),
+            self._f32(self.head_dist.weight) if sep else None, self._f32(self.head_dist.bias) if sep else None,
+            separated=sep)
+        if sep:
+            return logits, logits_dist, feats
+        return logits, feats
+
+    def predict_labels(self, x):
+        """models/maest.py:935-939."""
+        logits = self.forward(x)[0]
+        activations = torch.sigmoid(logits).mean(dim=0)
+        return activations.detach().cpu().numpy(), self.labels
+
+
+# ---------------------------------------------------------------------------------------------------
+# factory (models/maest.py:1151-1388, :1467-1569)
+# ---------------------------------------------------------------------------------------------------
+_ARCH_DEFAULT_T = {
+    "passt_deit_bd_p16_384": 998, "passt_s_swa_p16_128_ap476": 998,
+    "discogs-maest-10s-fs-129e": 625, "discogs-maest-10s-pw-129e": 625, "discogs-maest-10s-dw-75e": 625,
+    "discogs-maest-5s-pw-129e": 312, "discogs-maest-20s-pw-129e": 1250, "discogs-maest-30s-pw-129e": 1875,
+    "discogs-maest-30s-pw-73e-ts": 1875, "discogs-maest-30s-pw-129e-519l": 1875,
+}
+
+
+@maest_ing.capture
+def get_maest(arch, pretrained: bool = True, n_classes: int = 400, in_channels: int = 1, stride_f: int = 10,
+              stride_t: int = 10, input_f: int = 96, input_t: int = None, u_patchout: int = 0, s_patchout_t: int = 0,
+              s_patchout_f: int = 0, s_patchout_f_indices: tuple = (), s_patchout_f_interleaved: int = 0,
+              s_patchout_t_indices: tuple = (), s_patchout_t_interleaved: int = 0, distilled_type: str = "mean",
+              checkpoint: str = None, checkpoint_swa_weigts: bool = True, checkpoint_discard_head: bool = False,
+              op_dtype: str = "fp16"):
+    """Same signature / defaults / arch table as the reference (`op_dtype` is the only addition)."""
+    if arch not in _ARCH_DEFAULT_T:
+        raise NotImplementedError(f"model {arch} not implemented")        # models/maest.py:1530
+    if not input_t:
+        input_t = _ARCH_DEFAULT_T[arch]
+    stride = (stride_f, stride_t)
+    if arch != "passt_deit_bd_p16_384" and stride != (10, 10):
+        warnings.warn(f"This model was pre-trained with strides {(10, 10)}, but now you set (fstride,tstride) to {stride}.")
+    if arch == "discogs-maest-30s-pw-129e-519l" and n_classes != 519:
+        n_classes = 519                                                  # :1377-1379
+    if pretrained:
+        raise RuntimeError(
+            "pretrained=True needs the released checkpoints (network download through timm in the reference, "
+            "models/helpers/vit_helpers.py:257-267); pass pretrained=False and `checkpoint=<local .ckpt>` or load_state_dict().")
+    model = MAEST(u_patchout=u_patchout, s_patchout_t=s_patchout_t, s_patchout_f=s_patchout_f,
+                  s_patchout_f_indices=s_patchout_f_indices, s_patchout_f_interleaved=s_patchout_f_interleaved,
+                  s_patchout_t_indices=s_patchout_t_indices, s_patchout_t_interleaved=s_patchout_t_interleaved,
+                  img_size=(input_f, input_t), stride=stride, in_chans=in_channels, num_classes=n_classes,
+                  distilled_type=distilled_type, op_dtype=op_dtype)
+    if checkpoint:
+        state_dict = torch.load(checkpoint, map_location="cpu")["state_dict"]
+        replace_str = "net_swa." if checkpoint_swa_weigts else ""
+        state_dict = {k.replace(replace_str, ""): v for k, v in state_dict.items()}
+        if checkpoint_discard_head:
+            state_dict = {k: v for k, v in state_dict.items() if "head" not in k}
+        model.load_state_dict(state_dict, strict=False)
+    return model

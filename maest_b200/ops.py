@@ -1,0 +1,211 @@
+"""Torch-facing wrappers over the C ABI (one function per entry point of include/maest_b200.h).
+
+torch is used for device memory and streams only; all arithmetic happens in libmaest_b200.so.  Every wrapper
+requires CUDA tensors and raises if the library is unavailable — there is no eager/CPU fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+
+F16, BF16, F32 = _lib.F16, _lib.BF16, _lib.F32
+_TORCH2DT = {torch.float16: F16, torch.bfloat16: BF16, torch.float32: F32}
+_DT2TORCH = {F16: torch.float16, BF16: torch.bfloat16, F32: torch.float32}
+
+
+def op_dtype_code(dtype) -> int:
+    if isinstance(dtype, int):
+        return dtype
+    if isinstance(dtype, str):
+        dtype = {"fp16": torch.float16, "f16": torch.float16, "float16": torch.float16, "bf16": torch.bfloat16,
+                 "bfloat16": torch.bfloat16}[dtype]
+    return _TORCH2DT[dtype]
+
+
+def _need_cuda(*ts: torch.Tensor):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("maest_b200 runs on CUDA (sm_100a) only; got a CPU tensor — there is no CPU fallback")
+
+
+def _lib_for(t: torch.Tensor):
+    dev = t.device.index if t.device.index is not None else torch.cuda.current_device()
+    return _lib.init(dev)
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def logmel(wav: torch.Tensor) -> torch.Tensor:
+    """[B, S] (or [S]) fp32 CUDA waveform -> [B, 96, T] (or [96, T]) normalised log-mel."""
+    _need_cuda(wav)
+    squeeze = wav.dim() == 1
+    w = wav.reshape(1, -1) if squeeze else wav
+    if w.dtype != torch.float32:
+        w = w.float()
+    if w.stride(-1) != 1:
+        w = w.contiguous()
+    B, S = w.shape
+    T = 1 + S // 256
+    mel = torch.empty((B, 96, T), device=w.device, dtype=torch.float32)
+    with torch.cuda.device(w.device):
+        lib = _lib_for(w)
+        _lib.check(lib.maest_logmel_fwd(w.data_ptr(), B, S, w.stride(0), mel.data_ptr(), _stream()), "logmel")
+    return mel[0] if squeeze else mel
+
+
+def layernorm16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, op_dtype=F16,
+                save_stats: bool = False):
+    _need_cuda(x, w, b)
+    assert x.dtype == torch.float32 and x.shape[-1] == 768 and x.is_contiguous()
+    rows = x.numel() // 768
+    dt = op_dtype_code(op_dtype)
+    y = torch.empty(x.shape, device=x.device, dtype=_DT2TORCH[dt])
+    mean = rstd = None
+    if save_stats:
+        mean = torch.empty(rows, device=x.device, dtype=torch.float32)
+        rstd = torch.empty(rows, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        lib = _lib_for(x)
+        _lib.check(lib.maest_layernorm_fwd(x.data_ptr(), w.data_ptr(), b.data_ptr(), y.data_ptr(), dt, rows, float(eps),
+                                           _p(mean), _p(rstd), _stream()), "layernorm")
+    return (y, mean, rstd) if save_stats else y
+
+
+def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int,
+           resid: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None,
+           addend: Optional[torch.Tensor] = None, rows_per_group: int = 0, group_stride: int = 0,
+           row_offset: int = 0) -> torch.Tensor:
+    """out = epilogue(a @ w.T + bias).  a [M,K], w [N,K] 16-bit (same dtype), K contiguous."""
+    _need_cuda(a, w, bias, resid, out, addend)
+    assert a.dtype == w.dtype and a.dtype in (torch.float16, torch.bfloat16)
+    assert a.dim() == 2 and w.dim() == 2 and a.shape[1] == w.shape[1] and a.stride(1) == 1 and w.stride(1) == 1
+    M, K = a.shape
+    N = w.shape[0]
+    dt = _TORCH2DT[a.dtype]
+    if out is None:
+        odt = a.dtype if epilogue in (_lib.EPI_STORE16, _lib.EPI_GELU16) else torch.float32
+        out = torch.empty((M, N), device=a.device, dtype=odt)
+    if epilogue == _lib.EPI_RESID32 and resid is None:
+        resid = out
+    with torch.cuda.device(a.device):
+        lib = _lib_for(a)
+        _lib.check(lib.maest_linear_fwd(a.data_ptr(), a.stride(0), w.data_ptr(), w.stride(0), _p(bias), M, N, K, dt,
+                                        epilogue, out.data_ptr(), out.stride(-2), _p(resid), _p(addend),
+                                        rows_per_group, group_stride, row_offset, _stream()), "linear")
+    return out
+
+
+def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 0) -> torch.Tensor:
+    """qkv [B*N, 3*heads*64] 16-bit -> o [B*N, heads*64] 16-bit."""
+    _need_cuda(qkv)
+    assert qkv.is_contiguous() and qkv.shape == (B * N, 3 * heads * 64)
+    out = torch.empty((B * N, heads * 64), device=qkv.device, dtype=qkv.dtype)
+    with torch.cuda.device(qkv.device):
+        lib = _lib_for(qkv)
+        _lib.check(lib.maest_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, N, heads, _TORCH2DT[qkv.dtype], variant,
+                                           _stream()), "attention")
+    return out
+
+
+def cast16(src: torch.Tensor, op_dtype=F16) -> torch.Tensor:
+    _need_cuda(src)
+    s = src.detach().float().contiguous()
+    dt = op_dtype_code(op_dtype)
+    dst = torch.empty(s.shape, device=s.device, dtype=_DT2TORCH[dt])
+    with torch.cuda.device(s.device):
+        lib = _lib_for(s)
+        _lib.check(lib.maest_cast_to16(s.data_ptr(), dst.data_ptr(), s.numel(), dt, _stream()), "cast16")
+    return dst
+
+
+def keep_ft_tensor(keep_f: Optional[Sequence[int]], keep_t: Optional[Sequence[int]], Fp: int, Tp: int,
+                   keep_seq: Optional[Sequence[int]], device) -> Optional[torch.Tensor]:
+    """Kept patch-grid cells in sequence order as int32 (f << 16 | t); None when nothing is dropped."""
+    if keep_f is None and keep_t is None and keep_seq is None:
+        return None
+    f = torch.arange(Fp) if keep_f is None else torch.as_tensor(list(keep_f), dtype=torch.long)
+    t = torch.arange(Tp) if keep_t is None else torch.as_tensor(list(keep_t), dtype=torch.long)
+    ft = (f[:, None] * 65536 + t[None, :]).reshape(-1)
+    if keep_seq is not None:
+        ft = ft[torch.as_tensor(list(keep_seq), dtype=torch.long)]
+    return ft.to(torch.int32).to(device)
+
+
+def patch_tokens(mel: torch.Tensor, w_pe16: torch.Tensor, conv_bias, freq_pe, time_pe, cls_token, dist_token,
+                 new_pos_embed, keep_ft: Optional[torch.Tensor] = None, t_offset: int = 0) -> torch.Tensor:
+    """mel [B,96,T] (fp32|fp16) -> tokens fp32 [B, 2+P, 768].  Parameter tensors in the reference's shapes."""
+    _need_cuda(mel, w_pe16)
+    assert mel.dim() == 3 and mel.is_contiguous() and mel.dtype in (torch.float32, torch.float16)
+    B, Fm, T = mel.shape
+    Fp = (Fm - 16) // 10 + 1
+    Tp = (T - 16) // 10 + 1
+    Wt = time_pe.shape[-1]
+    P = Fp * Tp if keep_ft is None else int(keep_ft.numel())
+    tokens = torch.empty((B, 2 + P, 768), device=mel.device, dtype=torch.float32)
+    with torch.cuda.device(mel.device):
+        lib = _lib_for(mel)
+        ws_bytes = lib.maest_patch_workspace_bytes(B, P)
+        ws = torch.empty(ws_bytes, device=mel.device, dtype=torch.uint8)
+        _lib.check(lib.maest_patch_tokens_fwd(
+            mel.data_ptr(), _TORCH2DT[mel.dtype], B, T, w_pe16.data_ptr(), _TORCH2DT[w_pe16.dtype],
+            conv_bias.data_ptr(), freq_pe.data_ptr(), Fp, time_pe.data_ptr(), Wt, cls_token.data_ptr(),
+            dist_token.data_ptr(), new_pos_embed.data_ptr(), _p(keep_ft), P, int(t_offset), tokens.data_ptr(),
+            ws.data_ptr(), ws_bytes, _stream()), "patch_tokens")
+    return tokens
+
+
+def encoder(x: torch.Tensor, B: int, N: int, block_table, n_blocks: int, last_attn_only: bool, op_dtype,
+            attn_variant: int = 0, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Run n_blocks transformer blocks in place on the fp32 residual stream x [B*N, 768]."""
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    with torch.cuda.device(x.device):
+        lib = _lib_for(x)
+        need = lib.maest_encoder_workspace_bytes(B * N)
+        if workspace is None or workspace.numel() < need:
+            workspace = torch.empty(need, device=x.device, dtype=torch.uint8)
+        _lib.check(lib.maest_encoder_fwd(x.data_ptr(), B, N, block_table, n_blocks, int(bool(last_attn_only)),
+                                         op_dtype_code(op_dtype), attn_variant, workspace.data_ptr(),
+                                         workspace.numel(), _stream()), "encoder")
+    return x
+
+
+def pool_head(x: torch.Tensor, B: int, N: int, norm_w, norm_b, hln_w, hln_b, head_w, head_b, hdist_w=None,
+              hdist_b=None, separated: bool = False, save_ln: bool = False):
+    _need_cuda(x)
+    C_ = head_w.shape[0]
+    dev = x.device
+    logits = torch.empty((B, C_), device=dev, dtype=torch.float32)
+    logits_dist = torch.empty((B, C_), device=dev, dtype=torch.float32) if separated else None
+    feats = torch.empty((B, 768), device=dev, dtype=torch.float32)
+    ln_cls = torch.empty((B, 768), device=dev, dtype=torch.float32) if save_ln else None
+    ln_dist = torch.empty((B, 768), device=dev, dtype=torch.float32) if save_ln else None
+    with torch.cuda.device(dev):
+        lib = _lib_for(x)
+        _lib.check(lib.maest_pool_head_fwd(x.data_ptr(), B, N, norm_w.data_ptr(), norm_b.data_ptr(), hln_w.data_ptr(),
+                                           hln_b.data_ptr(), head_w.data_ptr(), head_b.data_ptr(), _p(hdist_w),
+                                           _p(hdist_b), C_, _lib.HEAD_SEPARATED if separated else _lib.HEAD_MEAN,
+                                           logits.data_ptr(), _p(logits_dist), feats.data_ptr(), _p(ln_cls),
+                                           _p(ln_dist), _stream()), "pool_head")
+    if save_ln:
+        return logits, logits_dist, feats, ln_cls, ln_dist
+    return logits, logits_dist, feats
+
+
+def block_embedding(x: torch.Tensor, B: int, N: int) -> torch.Tensor:
+    _need_cuda(x)
+    emb = torch.empty((B, 3 * 768), device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        lib = _lib_for(x)
+        _lib.check(lib.maest_block_embedding_fwd(x.data_ptr(), B, N, emb.data_ptr(), _stream()), "block_embedding")
+    return emb
