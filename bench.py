@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py — clips/sec of the MAEST hot path (waveform -> log-mel -> tokens -> 12 blocks -> logits) on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--arch ...] [--batch B]
+
+A "step" is one forward pass over one batch of synthetic clips (BASELINE.json configs[2]:
+discogs-maest-30s-pw-129e, batch 64, [64, 480000] 16 kHz waveforms -> 96x1876 mel -> 1685 tokens).  One process per
+GPU (torchrun for N>1); clips shard across ranks with no data-path collective (weak scaling: 64 clips per GPU).
+Rank 0 prints ONE JSON line.  `value` = whole-job clips/s with inputs resident in HBM; `e2e` = the same metric through
+the public API `model(waveform)` with the waveform in pinned host memory (H2D inside the timed region, logits read
+back to the host every step).  `roofline` describes the dominant kernel (the tcgen05 GEMM), timed with CUDA events.
+
+`--impl reference` times the CPU restatement of the reference (oracle/maest_oracle.py, torch CPU ops, all host
+threads) on a bounded sample of the same workload; the reference itself is pure Python under /root/reference, which does
+not exist on the GPU box, and the oracle is pinned against it by tests/golden.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ARCH_T = {"discogs-maest-30s-pw-129e": (480000, 187), "discogs-maest-10s-pw-129e": (160000, 62)}
+EMBED, DEPTH, HEADS, MLP = 768, 12, 12, 3072
+
+
+def flops_per_clip(N: int, P: int, C: int = 400):
+    lin = DEPTH * 2 * N * (EMBED * 3 * EMBED + EMBED * EMBED + 2 * EMBED * MLP)
+    att = DEPTH * 4 * N * N * EMBED
+    patch = 2 * P * 256 * EMBED
+    return dict(linear=lin, attention=att, patch=patch, head=2 * EMBED * C, total=lin + att + patch + 2 * EMBED * C)
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            d = json.load(f)
+        return dict(hbm_gbs=d["hbm_gbs"], bf16_tflops=d["bf16_tflops"], bf16_tflops_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    source="MEASURED_PEAKS.json")
+    return dict(hbm_gbs=6650.0, bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, gpu_index: int):
+        self.gpu = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "100", "-i", str(self.gpu)],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_oracle_clips_per_s(arch: str, clips: int, repeats: int = 1):
+    """Time the CPU restatement of the reference on `clips` clips of the workload (fp32, all host threads)."""
+    import torch
+    from maest_b200 import synth
+    from oracle import maest_oracle as O
+
+    S, grid_t = ARCH_T[arch]
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.synth_state_dict(grid_t, 400, seed=0)
+    x = synth.wave_a(clips, S)
+    best = float("inf")
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            O.forward(x, sd, img_t=(S // 256), dtype=torch.float32)
+            best = min(best, time.perf_counter() - t0)
+    return clips / best, torch.get_num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    from maest_b200 import synth
+    from oracle import maest_oracle as O
+
+    S, grid_t = ARCH_T[args.arch]
+    clips = args.ref_clips
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd = synth.synth_state_dict(grid_t, 400, seed=0)
+    x = synth.wave_a(clips, S)
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            O.forward(x, sd, img_t=S // 256, dtype=torch.float32)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            O.forward(x, sd, img_t=S // 256, dtype=torch.float32)
+        dt = time.perf_counter() - t0
+    val = clips * args.steps / dt
+    N = 2 + 9 * ((S // 256 + 1 - 16) // 10 + 1)
+    line = dict(metric="clips/sec", value=val, unit="clips/s", impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"{args.arch} inference, waveform [{clips},{S}] -> logits, N={N} tokens (bounded CPU sample of the batch-64 workload)"),
+                cpu_baseline=dict(value=val, unit="clips/s", cores=torch.get_num_threads(), kind="port",
+                                  sample=f"{clips} clips/step x {args.steps} steps, oracle/maest_oracle.py fp32 torch-CPU restatement of the reference"),
+                e2e=dict(value=val, unit="clips/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line), flush=True)
+
+
+def kernel_breakdown(model, wav, iters: int = 2):
+    """Per-kernel CUDA-event times of one step, composed at the ops level exactly like MAEST.forward."""
+    import torch
+    from maest_b200 import _lib, ops
+    acc = {}
+
+    def timed(name, fn):
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        out = fn()
+        b.record()
+        acc.setdefault(name, []).append((a, b))
+        return out
+
+    dt = model.op_dtype
+    for _ in range(iters):
+        mel = timed("logmel", lambda: ops.logmel(wav))
+        tok = timed("patch_tokens", lambda: model.tokens_from_mel(mel))
+        B, N, _ = tok.shape
+        x = tok.view(B * N, EMBED)
+        for i, blk in enumerate(model.blocks):
+            w = {k: model._weight16(f"blocks.{i}.{k}", p) for k, p in (("qkv", blk.attn.qkv.weight), ("proj", blk.attn.proj.weight),
+                                                                       ("fc1", blk.mlp.fc1.weight), ("fc2", blk.mlp.fc2.weight))}
+            h = timed("layernorm", lambda: ops.layernorm16(x, blk.norm1.weight.detach(), blk.norm1.bias.detach(), 1e-6, dt))
+            qkv = timed("gemm_qkv", lambda: ops.linear(h, w["qkv"], blk.attn.qkv.bias.detach(), _lib.EPI_STORE16))
+            o = timed("attention", lambda: ops.attention(qkv, B, N, HEADS, model.attn_variant))
+            timed("gemm_proj", lambda: ops.linear(o, w["proj"], blk.attn.proj.bias.detach(), _lib.EPI_RESID32, resid=x, out=x))
+            h = timed("layernorm", lambda: ops.layernorm16(x, blk.norm2.weight.detach(), blk.norm2.bias.detach(), 1e-6, dt))
+            u = timed("gemm_fc1", lambda: ops.linear(h, w["fc1"], blk.mlp.fc1.bias.detach(), _lib.EPI_GELU16))
+            timed("gemm_fc2", lambda: ops.linear(u, w["fc2"], blk.mlp.fc2.bias.detach(), _lib.EPI_RESID32, resid=x, out=x))
+            del h, qkv, o, u
+        timed("pool_head", lambda: ops.pool_head(tok, B, N, model.norm.weight.detach(), model.norm.bias.detach(), model.head[0].weight.detach(),
+                                                 model.head[0].bias.detach(), model.head[1].weight.detach(), model.head[1].bias.detach()))
+    torch.cuda.synchronize()
+    out = {}
+    for k, evs in acc.items():
+        ms = [a.elapsed_time(b) for a, b in evs]
+        per_iter = len(evs) // iters
+        out[k] = dict(launches_per_step=per_iter, ms_per_launch=sum(ms) / len(ms), ms_per_step=sum(ms) / iters)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--arch", default="discogs-maest-30s-pw-129e")
+    ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
+    ap.add_argument("--op-dtype", default="fp16", choices=["fp16", "bf16"])
+    ap.add_argument("--attn-variant", type=int, default=0)
+    ap.add_argument("--ref-clips", type=int, default=2, help="--impl reference: clips per step (bounded CPU sample)")
+    ap.add_argument("--cpu-baseline-clips", type=int, default=4)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-breakdown", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from maest_b200 import get_maest, synth
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (B200); there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    S, grid_t = ARCH_T[args.arch]
+    B = args.batch
+    model = get_maest(arch=args.arch, pretrained=False, op_dtype=args.op_dtype)
+    model.attn_variant = args.attn_variant
+    model.load_state_dict(synth.synth_state_dict(grid_t, 400, seed=0), strict=False)   # random-init weights (no checkpoints offline)
+    model = model.to(dev).eval()
+
+    g = torch.Generator(device=dev).manual_seed(1234 + rank)
+    wav_dev = torch.rand(B, S, generator=g, device=dev) * 2 - 1          # synthetic full-scale noise, resident in HBM
+    host = [torch.empty(B, S, dtype=torch.float32).pin_memory() for _ in range(2)]
+    for h in host:
+        h.copy_(wav_dev.cpu())
+    T = 1 + S // 256
+    P = 9 * ((T - 16) // 10 + 1)
+    N = 2 + P
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms: float) -> float:
+        if world == 1:
+            return ms
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    with torch.no_grad():
+        # ---------------- device-resident throughput ----------------
+        for _ in range(args.warmup):
+            model(wav_dev)
+        sampler = ClockSampler(local)
+        if rank == 0:
+            sampler.start()
+        barrier()
+        e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e0.record()
+        for _ in range(args.steps):
+            logits, _ = model(wav_dev)
+        e1.record()
+        barrier()
+        ms_dev = max_over_ranks(e0.elapsed_time(e1))
+
+        # ---------------- end-to-end through the public API, host buffers ----------------
+        copy_stream = torch.cuda.Stream(device=dev)
+        stage = [torch.empty(B, S, device=dev) for _ in range(2)]
+        ready = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+        out_host = torch.empty(B, 400, dtype=torch.float32).pin_memory()
+
+        def h2d(i):
+            with torch.cuda.stream(copy_stream):
+                copy_stream.wait_event(consumed[i % 2])
+                stage[i % 2].copy_(host[i % 2], non_blocking=True)
+                ready[i % 2].record(copy_stream)
+
+        def e2e_loop(steps):
+            for c in consumed:
+                c.record()
+            h2d(0)
+            for i in range(steps):
+                if i + 1 < steps:
+                    h2d(i + 1)
+                torch.cuda.current_stream().wait_event(ready[i % 2])
+                lo, _ = model(stage[i % 2])
+                consumed[i % 2].record()
+                out_host.copy_(lo, non_blocking=True)
+            torch.cuda.synchronize()
+
+        e2e_loop(2)
+        barrier()
+        e2, e3 = torch.cuda.Event(True), torch.cuda.Event(True)
+        e2.record()
+        e2e_loop(args.steps)
+        e3.record()
+        barrier()
+        ms_e2e = max_over_ranks(e2.elapsed_time(e3))
+        clocks = sampler.stop() if rank == 0 else None
+
+        breakdown = None
+        if rank == 0 and not args.no_breakdown:
+            breakdown = kernel_breakdown(model, wav_dev)
+
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = measured_peaks()
+    fl = flops_per_clip(N, P)
+    clips = B * world * args.steps
+    value = clips / (ms_dev / 1e3)
+    e2e_val = clips / (ms_e2e / 1e3)
+    per_step_launches = 4 + DEPTH * 7
+    line = dict(metric="clips/sec", value=value, unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                dtype=args.op_dtype + " operands, fp32 accumulate/residual/softmax/mel", data="synthetic",
+                config=dict(workload=f"{args.arch} inference, waveform [{B},{S}] per GPU -> 96x{T} log-mel -> {N} tokens -> 12 blocks -> logits[{B},400]",
+                            batch_per_gpu=B, tokens=N, weights="random-init (seeded, fp16/bf16-representable)",
+                            l2="per-step working set (>1.4 GB activations) exceeds the 126 MB L2; no explicit flush",
+                            gflop_per_clip=fl["total"] / 1e9),
+                e2e=dict(value=e2e_val, unit="clips/s", h2d_bytes_per_step=B * S * 4, d2h_bytes_per_step=B * 400 * 4,
+                         ms_per_step=ms_e2e / args.steps, note="pinned host waveform, double-buffered H2D on a copy stream, logits D2H every step"),
+                gpu_launches=per_step_launches * args.steps, clocks=clocks,
+                model_tflops=value / world * fl["total"] / 1e12, model_frac_of_bf16_sustained=value / world * fl["total"] / 1e12 / peaks["bf16_tflops_sustained"])
+    if breakdown:
+        gemm_ms = sum(v["ms_per_step"] for k, v in breakdown.items() if k.startswith("gemm_"))
+        gemm_launches = sum(v["launches_per_step"] for k, v in breakdown.items() if k.startswith("gemm_"))
+        gemm_flops = B * fl["linear"]
+        achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
+        total_ms = sum(v["ms_per_step"] for v in breakdown.values())
+        line["roofline"] = dict(bound="tensor", kernel="gemm_tn_kernel (qkv/proj/fc1/fc2, 48 launches per step)", achieved=achieved,
+                                peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"],
+                                traffic=None, peak_source=peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                                share_of_step=gemm_ms / total_ms, launches_per_step=gemm_launches)
+        att = breakdown.get("attention")
+        if att:
+            a_tf = B * fl["attention"] / (att["ms_per_step"] / 1e3) / 1e12
+            line["attention"] = dict(achieved=a_tf, unit="TFLOP/s", frac=a_tf / peaks["bf16_tflops_sustained"], share_of_step=att["ms_per_step"] / total_ms)
+        lm = breakdown.get("logmel")
+        pt = breakdown.get("patch_tokens")
+        if lm and pt:
+            by = B * (4 * S + 2 * N * EMBED)
+            gbs = by / ((lm["ms_per_step"] + pt["ms_per_step"]) / 1e3) / 1e9
+            line["mel_patch_stage"] = dict(bound="hbm", achieved=gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbs / peaks["hbm_gbs"],
+                                           algorithmic_bytes_per_clip=4 * S + 2 * N * EMBED)
+        line["breakdown_ms_per_step"] = {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()}
+    if not args.no_cpu_baseline:
+        v, cores = cpu_oracle_clips_per_s(args.arch, args.cpu_baseline_clips)
+        line["cpu_baseline"] = dict(value=v, unit="clips/s", cores=cores, kind="port",
+                                    sample=f"{args.cpu_baseline_clips} clips of the same workload, oracle/maest_oracle.py (torch-CPU fp32 restatement of the reference), 1 run")
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

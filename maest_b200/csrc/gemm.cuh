@@ -3,7 +3,9 @@
 //   warp 0      TMA producer   (cp.async.bulk.tensor, SWIZZLE_128B, 4-stage mbarrier ring)
 //   warp 1      MMA issuer     (one elected lane: tcgen05.mma cta_group::1 kind::f16, 128x256x16, fp32 accum in TMEM)
 //   warp 2      TMEM allocator (512 columns = two 128x256 fp32 accumulators, double-buffered against the epilogue)
-//   warps 4..7  epilogue       (tcgen05.ld 32x32b, one accumulator row per thread, fused bias/GELU/residual/pos-embed)
+//   warps 4..11 epilogue       (8 warps: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4; tcgen05.ld 32x32b gives
+//                               one accumulator row per thread; rows are transposed through a per-warp XOR-swizzled smem
+//                               tile so that bias/GELU/residual/pos-embed math and ALL global traffic are row-coalesced)
 //
 // Replaces the cuBLAS(Lt)/cuDNN calls behind models/maest.py:250 (patch-embed conv as GEMM), :361 (qkv),
 // :376 (proj), :203-206 (fc1, GELU, fc2) and the separate bias / residual-add / pos-embed passes (:418-419, :670-675).
@@ -16,11 +18,13 @@ constexpr int GEMM_BM = 128;
 constexpr int GEMM_BN = 256;
 constexpr int GEMM_BK = 64;
 constexpr int GEMM_STAGES = 4;
-constexpr int GEMM_THREADS = 256;
+constexpr int GEMM_THREADS = 384;
+constexpr int GEMM_EPI_WARPS = 8;
+constexpr int GEMM_STG_BYTES = 32 * 32 * 4;        // per-epilogue-warp staging tile: 32 rows x 32 fp32
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;  // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
-constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+constexpr int GEMM_SMEM_BYTES = GEMM_STAGES * GEMM_STAGE_BYTES + GEMM_EPI_WARPS * GEMM_STG_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
 
 enum : int {
   EPI_STORE16 = 0,  // out16[r,n] = acc + bias[n]
@@ -63,7 +67,8 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
                const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + GEMM_STAGES * GEMM_STAGE_BYTES);
+  uint8_t* stg_base = smem + GEMM_STAGES * GEMM_STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + GEMM_EPI_WARPS * GEMM_STG_BYTES);
   uint64_t* full_bar = bars;                       // [STAGES]
   uint64_t* empty_bar = bars + GEMM_STAGES;        // [STAGES]
   uint64_t* tfull_bar = bars + 2 * GEMM_STAGES;    // [2]
@@ -88,7 +93,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 128);
+      mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * 32);
     }
     fence_mbar_init();
   }
@@ -147,79 +152,79 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
   } else if (warp >= 4) {
     using O = Op16<DT == DT_BF16 ? DT_BF16 : DT_F16>;
-    const int q = warp & 3;  // TMEM lane quarter owned by this warp
+    const int e = warp - 4;
+    const int q = warp & 3;        // TMEM lane quarter this warp may access
+    const int half = e >> 2;       // which 128 accumulator columns this warp drains
+    uint8_t* stg = stg_base + e * GEMM_STG_BYTES;
+    const bool identity_rows = p.rows_per_group >= p.M;
+    const int sub_row = lane >> 3;  // coalesced phase: 4 rows per instruction, 8 lanes x 16 B per row
+    const int c4 = lane & 7;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / num_n) * GEMM_BM;
-      const int n0 = (t % num_n) * GEMM_BN;
-      const int m = m0 + q * 32 + lane;
-      const bool row_ok = m < p.M;
-      long r = 0;
-      int pr = 0;
-      if (row_ok) {
-        pr = m % p.rows_per_group;
-        r = long(m / p.rows_per_group) * p.group_stride + p.row_offset + pr;
-      }
+      const int m0 = (t / num_n) * GEMM_BM + q * 32;
+      const int n0 = (t % num_n) * GEMM_BN + half * 128;
+      int nchunks = (p.N - n0 + 31) / 32;
+      nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN + half * 128);
+      if (nchunks == 0) {
+        tc_fence_before();
+        mbar_arrive(&tempty_bar[as]);
+      }
 #pragma unroll 1
-      for (int c = 0; c < GEMM_BN / 32; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= p.N) break;  // warp-uniform
+      for (int cc = 0; cc < nchunks; ++cc) {
+        const int n = n0 + cc * 32;
         uint32_t v[32];
-        tmem_ld32(taddr + uint32_t(c * 32), v);
+        tmem_ld32(taddr + uint32_t(cc * 32), v);
         tc_wait_ld();
-        float f[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n + j));
-            f[j] += b4.x; f[j + 1] += b4.y; f[j + 2] += b4.z; f[j + 3] += b4.w;
-          }
+        if (cc == nchunks - 1) {   // accumulator fully drained by this warp: hand the TMEM stage back early
+          tc_fence_before();
+          mbar_arrive(&tempty_bar[as]);
         }
-        if (row_ok) {
+        __syncwarp();              // previous chunk's staging reads are complete
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+        }
+        __syncwarp();
+        const int col = n + c4 * 4;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + sub_row;
+          float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+          const int m = m0 + rl;
+          if (m >= p.M) continue;
+          long r;
+          int pr = 0;
+          if (identity_rows) { r = m; pr = m; }
+          else { pr = m % p.rows_per_group; r = long(m / p.rows_per_group) * p.group_stride + p.row_offset + pr; }
+          a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
           if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
             if constexpr (EPI == EPI_GELU16) {
-#pragma unroll
-              for (int j = 0; j < 32; ++j) f[j] = gelu_erf_fast(f[j]);
+              a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
             }
-            typename O::T* dst = reinterpret_cast<typename O::T*>(p.out) + r * p.ld_out + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 8) {
-              st_global_v4(dst + j, O::pack(f[j], f[j + 1]), O::pack(f[j + 2], f[j + 3]),
-                           O::pack(f[j + 4], f[j + 5]), O::pack(f[j + 6], f[j + 7]));
-            }
+            uint2 o;
+            o.x = O::pack(a.x, a.y);
+            o.y = O::pack(a.z, a.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.out) + r * p.ld_out + col) = o;
           } else if constexpr (EPI == EPI_RESID32) {
-            const float* src = p.resid + r * p.ld_out + n;
-            float* dst = reinterpret_cast<float*>(p.out) + r * p.ld_out + n;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 x4 = *reinterpret_cast<const float4*>(src + j);
-              float4 o4;
-              o4.x = x4.x + f[j]; o4.y = x4.y + f[j + 1]; o4.z = x4.z + f[j + 2]; o4.w = x4.w + f[j + 3];
-              *reinterpret_cast<float4*>(dst + j) = o4;
-            }
+            const float4 x4 = *reinterpret_cast<const float4*>(p.resid + r * p.ld_out + col);
+            a.x += x4.x; a.y += x4.y; a.z += x4.z; a.w += x4.w;
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
           } else {
-            float* dst = reinterpret_cast<float*>(p.out) + r * p.ld_out + n;
-            const float* add = p.addend ? p.addend + long(pr) * p.N + n : nullptr;
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o4 = make_float4(f[j], f[j + 1], f[j + 2], f[j + 3]);
-              if (add) {
-                const float4 a4 = __ldg(reinterpret_cast<const float4*>(add + j));
-                o4.x += a4.x; o4.y += a4.y; o4.z += a4.z; o4.w += a4.w;
-              }
-              *reinterpret_cast<float4*>(dst + j) = o4;
+            if (p.addend != nullptr) {
+              const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.addend + long(pr) * p.N + col));
+              a.x += d4.x; a.y += d4.y; a.z += d4.z; a.w += d4.w;
             }
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
           }
         }
       }
-      tc_fence_before();
-      mbar_arrive(&tempty_bar[as]);
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }

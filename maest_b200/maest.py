@@ -413,6 +413,8 @@ class MAEST(nn.Module):
         """Same contract as the reference's MAEST.forward (models/maest.py:831-933)."""
         assert isinstance(x, torch.Tensor), "Input must be a torch.Tensor"
         assert x.nelement() > 0, "Input tensor must not be empty"
+        if x.dim() == 1:
+            assert melspectrogram_input is False, "Input is 1D, but melspectrogram_input is True. This is not supported."
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("maest_b200: move the model to a CUDA device (B200, sm_100a); there is no CPU path")
@@ -422,7 +424,6 @@ class MAEST(nn.Module):
         img_t = self.img_size[1]
 
         if x.dim() == 1:
-            assert melspectrogram_input is False, "Input is 1D, but melspectrogram_input is True. This is not supported."
             m = self.melspectrogram(x)                               # [96, T]
             if m.shape[1] >= img_t:
                 trim = m.shape[1] % img_t

@@ -169,6 +169,16 @@ def main():
     assert g["head_dist.weight"] is None
     out["c4"] = d4
 
+    # state-dict contract (names + shapes) of the reference models
+    import json
+    contract = {}
+    for arch, n_cls in (("discogs-maest-30s-pw-129e", 400), ("discogs-maest-10s-fs-129e", 400), ("discogs-maest-5s-pw-129e", 400),
+                        ("discogs-maest-20s-pw-129e", 400), ("discogs-maest-30s-pw-129e-519l", 400), ("passt_s_swa_p16_128_ap476", 400)):
+        n = ref.get_maest(arch=arch, pretrained=False, n_classes=n_cls)
+        contract[arch] = {k: list(v.shape) for k, v in n.state_dict().items()}
+    with open(os.path.join(HERE, "state_dict_contract.json"), "w") as f:
+        json.dump(contract, f)
+
     for name, d in out.items():
         path = os.path.join(HERE, f"{name}.npz")
         np.savez_compressed(path, **d)
