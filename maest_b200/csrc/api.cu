@@ -165,9 +165,10 @@ int32_t maest_linear_fwd(const void* a, int64_t lda, const void* w, int64_t ldw,
   if ((r = make_tmap(&tb, w, op_dtype, N, K, ldw, GEMM_BN))) return r;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = addend; p.ld_out = int(ld_out);
-  if (rows_per_group <= 0) { p.rows_per_group = M; p.group_stride = 0; p.row_offset = 0; }
+  if (rows_per_group <= 0) { p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0; }
   else { p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; }
   if (epilogue == MAEST_EPI_RESID32 && !resid) return fail(-1, "linear: RESID32 needs resid");
+  if (epilogue == MAEST_EPI_RESID32 && rows_per_group > 0) return fail(-1, "linear: RESID32 does not support row remapping");
   cudaStream_t st = (cudaStream_t)stream;
   return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, ta, tb, p, st)
                                 : launch_gemm_dt<DT_F16>(epilogue, ta, tb, p, st);

@@ -219,20 +219,31 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
       }
       // pass 2: p = exp2(s*sc - m), row sum, P -> 16-bit
       const float neg_m = -m_run;
+      const bool full_tile = valid >= ATT_BKV;   // warp-uniform: only the last KV tile of a clip needs key masking
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         uint32_t v[32];
         tmem_ld32(tS + lane_off + uint32_t(c * 32), v);
         tc_wait_ld();
         uint32_t pk[16];
+        if (full_tile) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));
-          float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
-          if (c * 32 + i >= valid) p0 = 0.f;
-          if (c * 32 + i + 1 >= valid) p1 = 0.f;
-          l_run += p0 + p1;
-          pk[i >> 1] = O16::pack(p0, p1);
+          for (int i = 0; i < 32; i += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
+            l_run += p0 + p1;
+            pk[i >> 1] = O16::pack(p0, p1);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; i += 2) {
+            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));
+            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
+            if (c * 32 + i >= valid) p0 = 0.f;
+            if (c * 32 + i + 1 >= valid) p1 = 0.f;
+            l_run += p0 + p1;
+            pk[i >> 1] = O16::pack(p0, p1);
+          }
         }
         if constexpr (P_IN_TMEM) {
           tmem_st16(tP + lane_off + uint32_t(c * 16), pk);

@@ -93,12 +93,13 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Spin with a wall-clock bound (2 s): a protocol bug traps instead of hanging the GPU box.
 __device__ __forceinline__ uint64_t global_ns() {
   uint64_t t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
+#ifdef MB_SAFE_WAIT
+// Bring-up build (-DMB_SAFE_WAIT): spin with a wall-clock bound (2 s) so a protocol bug traps instead of hanging the box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t n = 0;
   uint64_t t0 = 0;
@@ -114,6 +115,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+#else
+// Production wait: two instructions per retry (SYNCS.TRYWAIT + BRA) and a long hardware suspend hint, so waiting
+// threads do not steal issue slots from the math warps that share their SM sub-partition.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "MB_WAIT_LOOP:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
+      "@P1 bra MB_WAIT_DONE;\n\t"
+      "bra MB_WAIT_LOOP;\n\t"
+      "MB_WAIT_DONE:\n\t}\n" ::"r"(smem_u32(bar)),
+      "r"(parity), "r"(0x989680u)
+      : "memory");
+}
+#endif
 
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {

@@ -46,15 +46,25 @@ struct GemmParams {
 
 // exact-erf GELU (models/maest.py:500 nn.GELU default).  erf via Abramowitz-Stegun 7.1.26
 // (|abs err| <= 1.5e-7, below fp32 epsilon of the 0.5*x*(1+erf) product for |x| < 1).
+__device__ __forceinline__ float rcp_approx(float x) {
+  float y;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ float ex2_approx_ftz(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 __device__ __forceinline__ float gelu_erf_fast(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __frcp_rn(fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));          // MUFU.RCP (1 ulp-ish; erf error budget is 1.5e-7)
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = exp2f(-1.4426950408889634f * z * z);
+  const float e = ex2_approx_ftz(-1.4426950408889634f * z * z);   // MUFU.EX2
   const float erf_abs = fmaf(-p, e, 1.0f);
   const float erf_v = copysignf(erf_abs, x);
   const float hx = 0.5f * x;
@@ -156,7 +166,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     const int q = warp & 3;        // TMEM lane quarter this warp may access
     const int half = e >> 2;       // which 128 accumulator columns this warp drains
     uint8_t* stg = stg_base + e * GEMM_STG_BYTES;
-    const bool identity_rows = p.rows_per_group >= p.M;
+    const bool identity_rows = p.rows_per_group == 0x7fffffff;   // set by the host when no remap is requested
     const int sub_row = lane >> 3;  // coalesced phase: 4 rows per instruction, 8 lanes x 16 B per row
     const int c4 = lane & 7;
     int as = 0;
@@ -166,9 +176,24 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int n0 = (t % num_n) * GEMM_BN + half * 128;
       int nchunks = (p.N - n0 + 31) / 32;
       nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
+      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN + half * 128);
+      // RESID32: the residual tile does not depend on the accumulator, so its global loads are issued one chunk
+      // ahead (and, for chunk 0, before waiting for the accumulator) to keep HBM requests in flight.
+      float4 xr[8];
+      auto load_resid = [&](int cc) {
+        if constexpr (EPI == EPI_RESID32) {
+          const int col = n0 + cc * 32 + c4 * 4;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int m = m0 + i * 4 + sub_row;
+            xr[i] = (m < p.M && cc < nchunks) ? *reinterpret_cast<const float4*>(p.resid + long(m) * p.ld_out + col)
+                                              : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      };
+      load_resid(0);
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN + half * 128);
       if (nchunks == 0) {
         tc_fence_before();
         mbar_arrive(&tempty_bar[as]);
@@ -193,17 +218,26 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         const int col = n + c4 * 4;
         float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+        float4 acc4[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int rl = i * 4 + sub_row;
           float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+          a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+          if constexpr (EPI == EPI_RESID32) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
+          acc4[i] = a;
+        }
+        if constexpr (EPI == EPI_RESID32) load_resid(cc + 1);   // next chunk's residual is in flight during the stores
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int rl = i * 4 + sub_row;
+          float4 a = acc4[i];
           const int m = m0 + rl;
           if (m >= p.M) continue;
           long r;
           int pr = 0;
-          if (identity_rows) { r = m; pr = m; }
+          if (identity_rows) { r = m; }
           else { pr = m % p.rows_per_group; r = long(m / p.rows_per_group) * p.group_stride + p.row_offset + pr; }
-          a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
           if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
             if constexpr (EPI == EPI_GELU16) {
               a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
@@ -213,8 +247,6 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
             o.y = O::pack(a.z, a.w);
             *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.out) + r * p.ld_out + col) = o;
           } else if constexpr (EPI == EPI_RESID32) {
-            const float4 x4 = *reinterpret_cast<const float4*>(p.resid + r * p.ld_out + col);
-            a.x += x4.x; a.y += x4.y; a.z += x4.z; a.w += x4.w;
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
           } else {
             if (p.addend != nullptr) {
