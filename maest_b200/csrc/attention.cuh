@@ -58,12 +58,15 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
   uint8_t* sP = smem + ATT_TILE_BYTES * (1 + 2 * ATT_KV_STAGES);    // SS mode only: two [128 x 64] halves
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + att_smem_bytes<P_IN_TMEM>() - 128);
   uint64_t* q_full = bars;            // 1
-  uint64_t* kv_full = bars + 1;       // [2]
-  uint64_t* kv_empty = bars + 3;      // [2]
-  uint64_t* s_full = bars + 5;        // 1
-  uint64_t* p_full = bars + 6;        // 1 (count 128)
-  uint64_t* o_done = bars + 7;        // 1
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* k_full = bars + 1;        // [2]
+  uint64_t* k_empty = bars + 3;       // [2]
+  uint64_t* v_full = bars + 5;        // [2]
+  uint64_t* v_empty = bars + 7;       // [2]
+  uint64_t* s_full = bars + 9;        // S_j written by the tensor pipe
+  uint64_t* s_free = bars + 10;       // S_j copied to registers by all 128 softmax threads (count 128)
+  uint64_t* p_full = bars + 11;       // P_j written (count 128)
+  uint64_t* o_done = bars + 12;       // O += P_j V_j retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -80,10 +83,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
   if (warp == 5 && lane == 0) {
     mbar_init(q_full, 1);
     for (int i = 0; i < ATT_KV_STAGES; ++i) {
-      mbar_init(&kv_full[i], 1);
-      mbar_init(&kv_empty[i], 1);
+      mbar_init(&k_full[i], 1);
+      mbar_init(&k_empty[i], 1);
+      mbar_init(&v_full[i], 1);
+      mbar_init(&v_empty[i], 1);
     }
     mbar_init(s_full, 1);
+    mbar_init(s_free, 128);
     mbar_init(p_full, 128);
     mbar_init(o_done, 1);
     fence_mbar_init();
@@ -107,11 +113,13 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(&kv_empty[stage], phase ^ 1);
-        mbar_expect_tx(&kv_full[stage], 2 * ATT_TILE_BYTES);
         const int r = row_base + j * ATT_BKV;
-        tma_load_2d(sK + stage * ATT_TILE_BYTES, &tmap_qkv, &kv_full[stage], p.H * ATT_D + h * ATT_D, r);
-        tma_load_2d(sV + stage * ATT_TILE_BYTES, &tmap_qkv, &kv_full[stage], 2 * p.H * ATT_D + h * ATT_D, r);
+        mbar_wait(&k_empty[stage], phase ^ 1);
+        mbar_expect_tx(&k_full[stage], ATT_TILE_BYTES);
+        tma_load_2d(sK + stage * ATT_TILE_BYTES, &tmap_qkv, &k_full[stage], p.H * ATT_D + h * ATT_D, r);
+        mbar_wait(&v_empty[stage], phase ^ 1);
+        mbar_expect_tx(&v_full[stage], ATT_TILE_BYTES);
+        tma_load_2d(sV + stage * ATT_TILE_BYTES, &tmap_qkv, &v_full[stage], 2 * p.H * ATT_D + h * ATT_D, r);
         if (++stage == ATT_KV_STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -125,25 +133,29 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
 #pragma unroll
         for (int k = 0; k < ATT_D / 16; ++k)
           mma_ss(tS, qdesc + uint64_t(2 * k), kdesc + uint64_t(2 * k), idesc_qk, k ? 1u : 0u);
+        tc_commit(&k_empty[stage]);   // K stage reusable once S = Q K^T has retired
         tc_commit(s_full);
       };
       mbar_wait(q_full, 0);
-      mbar_wait(&kv_full[0], 0);
+      mbar_wait(&k_full[0], 0);
       tc_fence_after();
       issue_qk(0);
       int stage = 0;
       uint32_t phase = 0;
       for (int j = 0; j < nkv; ++j) {
-        mbar_wait(p_full, j & 1);   // P_j written, S_j consumed
-        tc_fence_after();
         int nstage = stage + 1;
         uint32_t nphase = phase;
         if (nstage == ATT_KV_STAGES) { nstage = 0; nphase ^= 1; }
         if (j + 1 < nkv) {
-          mbar_wait(&kv_full[nstage], nphase);
+          // S_j lives in the softmax threads' registers now: overwrite it with S_{j+1} while they exponentiate
+          mbar_wait(s_free, j & 1);
+          mbar_wait(&k_full[nstage], nphase);
           tc_fence_after();
           issue_qk(nstage);
         }
+        mbar_wait(p_full, j & 1);
+        mbar_wait(&v_full[stage], phase);
+        tc_fence_after();
         // O (+)= P_j V_j : 8 K-steps of 16 keys
         const uint32_t vbase = smem_u32(sV + stage * ATT_TILE_BYTES);
 #pragma unroll
@@ -156,7 +168,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
             mma_ss(tO, pdesc, vdesc, idesc_pv, (j | k) ? 1u : 0u);
           }
         }
-        tc_commit(&kv_empty[stage]);
+        tc_commit(&v_empty[stage]);
         tc_commit(o_done);
         stage = nstage;
         phase = nphase;
@@ -172,22 +184,25 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
     for (int j = 0; j < nkv; ++j) {
       const int kv0 = j * ATT_BKV;
       const int valid = p.N - kv0;  // keys [0, valid) of this tile are real (>=128 when not the last tile)
+      const bool full_tile = valid >= ATT_BKV;
       mbar_wait(s_full, j & 1);
       tc_fence_after();
-      // pass 1: row max
+      // the whole score row goes to registers in one shot; the TMEM columns are handed back immediately
+      uint32_t s[128];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) tmem_ld32(tS + lane_off + uint32_t(c * 32), *reinterpret_cast<uint32_t(*)[32]>(s + 32 * c));
+      tc_wait_ld();
+      tc_fence_before();
+      mbar_arrive(s_free);
       float mt = -INFINITY;
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + uint32_t(c * 32), v);
-        tc_wait_ld();
-        if (valid >= (c + 1) * 32) {
+      if (full_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mt = fmaxf(mt, __uint_as_float(v[i]));
-        } else {
+        for (int i = 0; i < 128; ++i) mt = fmaxf(mt, __uint_as_float(s[i]));
+      } else {
 #pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (c * 32 + i < valid) mt = fmaxf(mt, __uint_as_float(v[i]));
+        for (int i = 0; i < 128; ++i) {
+          if (i >= valid) s[i] = 0xff800000u;   // -inf: masked keys contribute exp2(-inf) = 0
+          mt = fmaxf(mt, __uint_as_float(s[i]));
         }
       }
       const float mt_sc = mt * sc;
@@ -217,33 +232,19 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
       } else {
         m_run = mt_sc;
       }
-      // pass 2: p = exp2(s*sc - m), row sum, P -> 16-bit
+      // p = exp2(s*sc - m), row sum, P -> 16-bit
       const float neg_m = -m_run;
-      const bool full_tile = valid >= ATT_BKV;   // warp-uniform: only the last KV tile of a clip needs key masking
-#pragma unroll 1
+      float l0 = 0.f, l1 = 0.f;
+#pragma unroll
       for (int c = 0; c < 4; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tS + lane_off + uint32_t(c * 32), v);
-        tc_wait_ld();
         uint32_t pk[16];
-        if (full_tile) {
 #pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
-            l_run += p0 + p1;
-            pk[i >> 1] = O16::pack(p0, p1);
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            float p0 = ex2_approx(fmaf(__uint_as_float(v[i]), sc, neg_m));
-            float p1 = ex2_approx(fmaf(__uint_as_float(v[i + 1]), sc, neg_m));
-            if (c * 32 + i >= valid) p0 = 0.f;
-            if (c * 32 + i + 1 >= valid) p1 = 0.f;
-            l_run += p0 + p1;
-            pk[i >> 1] = O16::pack(p0, p1);
-          }
+        for (int i = 0; i < 32; i += 2) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i]), sc, neg_m));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(s[c * 32 + i + 1]), sc, neg_m));
+          l0 += p0;
+          l1 += p1;
+          pk[i >> 1] = O16::pack(p0, p1);
         }
         if constexpr (P_IN_TMEM) {
           tmem_st16(tP + lane_off + uint32_t(c * 16), pk);
@@ -258,6 +259,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
           }
         }
       }
+      l_run += l0 + l1;
       if constexpr (P_IN_TMEM) tc_wait_st();
       else fence_proxy_async_smem();
       tc_fence_before();
