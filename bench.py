@@ -187,6 +187,85 @@ def kernel_breakdown(model, wav, iters: int = 2):
     return out
 
 
+def run_train(args):
+    """configs[3]: maest_30s_from_passt_pretrain training step (mel [B,1,96,1875] fp16 in, s_patchout_t=90 -> 866 tokens,
+    mixup 0.3, BCE), bf16 operands, fwd + bwd + gradient all-reduce (N>1) + AdamW step inside the timed region."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from maest_b200 import get_maest, synth
+    from maest_b200.module import Module, allreduce_gradients
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    op = "bf16" if args.op_dtype == "fp16" and not os.environ.get("MAEST_TRAIN_FP16") else args.op_dtype
+    net = get_maest(arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=400, input_f=96, input_t=1875, s_patchout_t=90, op_dtype=op)
+    net.load_state_dict(synth.synth_state_dict(187, 400, seed=0), strict=False)
+    mod = Module(net=net, mixup_alpha=0.3, do_swa=False).to(dev).train()
+    opt = torch.optim.AdamW(mod.parameters(), lr=2e-5, weight_decay=1e-4, fused=True)
+    torch.manual_seed(1 + rank)
+    np.random.seed(1 + rank)
+    g = torch.Generator(device=dev).manual_seed(7 + rank)
+    x = (0.5 * torch.randn(B, 1, 96, 1875, generator=g, device=dev)).half()
+    y = (torch.rand(B, 400, generator=g, device=dev) > 0.99).half()
+    batch = (x, ["clip"] * B, y)
+    n_grad = [0]
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = mod.training_step(batch, 0)
+        loss.backward()
+        if world > 1:
+            n_grad[0] = allreduce_gradients(mod)
+        opt.step()
+        return loss
+
+    for _ in range(args.warmup):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if rank == 0 else None
+    if rank == 0:
+        N, P = 866, 864
+        fl = flops_per_clip(N, P)
+        peaks = measured_peaks()
+        value = B * world * args.steps / (ms / 1e3)
+        tf = value / world * 3 * fl["total"] / 1e12
+        line = dict(metric="clips/sec (training step)", value=value, unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                    dtype=op + " operands, fp32 master weights/accumulate/residual/softmax", data="synthetic", mode="train",
+                    config=dict(workload=f"maest_30s_from_passt_pretrain training step: mel [{B},1,96,1875] fp16 per GPU, s_patchout_t=90 -> {N} tokens, "
+                                         "mixup 0.3, BCE, fwd+bwd" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + AdamW step",
+                                batch_per_gpu=B, tokens=N, gflop_per_clip_fwd=fl["total"] / 1e9),
+                    loss=float(loss), grad_elements_allreduced=n_grad[0], clocks=clocks,
+                    model_tflops=tf, model_frac_of_bf16_sustained=tf / peaks["bf16_tflops_sustained"],
+                    gpu_launches=args.steps * (12 * 30 + 12))
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -201,11 +280,15 @@ def main():
     ap.add_argument("--cpu-baseline-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
+                    help="infer: BASELINE.json configs[2] (headline).  train: configs[3], one optimisation step per 'step'")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     if args.impl == "reference":
         return run_reference(args)
+    if args.mode == "train":
+        return run_train(args)
 
     import torch
     import torch.distributed as dist

@@ -29,7 +29,9 @@ enum {
   MAEST_EPI_STORE16 = 0, /* out16 = A W^T + bias                                   (qkv: models/maest.py:361)            */
   MAEST_EPI_GELU16 = 1,  /* out16 = gelu_erf(A W^T + bias)                         (fc1+GELU: models/maest.py:203-204)   */
   MAEST_EPI_RESID32 = 2, /* out32 = resid32 + A W^T + bias                         (proj/fc2 + residual: :376,:206,:418-419) */
-  MAEST_EPI_STORE32 = 3  /* out32 = A W^T + bias (+ addend table, + row remap)     (patch-embed + pos-embed: :250,:670-675) */
+  MAEST_EPI_STORE32 = 3, /* out32 = A W^T + bias (+ addend table, + row remap)     (patch-embed + pos-embed: :250,:670-675) */
+  MAEST_EPI_GELUBWD16 = 4, /* out16 = (A B^T) * gelu'(aux16)    (autograd of mlp.act + mlp.fc2, models/maest.py:204-206)           */
+  MAEST_EPI_ATOMIC32 = 5   /* out32 += A B^T (split-K, atomics)  (weight gradients; autograd of every nn.Linear / the conv)        */
 };
 
 /* pooling modes (maest_pool_head_fwd) */
@@ -90,10 +92,22 @@ int32_t maest_linear_fwd(const void* a, int64_t lda, const void* w, int64_t ldw,
                          const float* resid, const float* addend, int32_t rows_per_group, int32_t group_stride,
                          int32_t row_offset, void* stream);
 
+/* General tcgen05 GEMM used by the training step: out = epilogue(sum_k A(m,k) B(n,k)).
+ *   a_mn = 0: A is [M, K] with K contiguous;  a_mn = 1: A is stored [K, M] with M contiguous (e.g. dY for a weight gradient)
+ *   b_mn = 0: B is [N, K] with K contiguous;  b_mn = 1: B is stored [K, N] with N contiguous (e.g. W for an input gradient)
+ * so forward (0,0), input-gradient (0,1) and weight-gradient (1,1) GEMMs all read activations, gradients and weights in their
+ * natural layouts.  aux16: MAEST_EPI_GELU16 optional 2nd output (pre-activation); MAEST_EPI_GELUBWD16 input.
+ * k_splits > 1 splits the reduction across CTAs (MAEST_EPI_ATOMIC32 only). */
+int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int64_t ldb, int32_t b_mn, const float* bias,
+                   int32_t M, int32_t N, int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out,
+                   const float* resid, const float* addend, int32_t rows_per_group, int32_t group_stride,
+                   int32_t row_offset, void* aux16, int32_t k_splits, void* stream);
+
 /* Fused multi-head attention, d_head 64.  Replaces Attention.forward lines models/maest.py:362-375.
  * qkv op16 [B*N, 3*H*64] as written by the qkv linear (columns = [q|k|v][head][64]); out op16 [B*N, H*64].
- * variant: 0 = P kept in TMEM (tcgen05.mma A-from-TMEM), 1 = P staged through shared memory. */
-int32_t maest_attention_fwd(const void* qkv, void* out, int32_t B, int32_t N, int32_t H, int32_t op_dtype,
+ * variant: 0 = P kept in TMEM (tcgen05.mma A-from-TMEM), 1 = P staged through shared memory.
+ * lse: optional fp32 [B, H, N] (may be NULL): per-row max + log2(sum) in the scaled log2 domain, saved for the backward pass. */
+int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t op_dtype,
                             int32_t variant, void* stream);
 
 /* The 12-block encoder on the fp32 residual stream x [B*N, 768], in place.  Replaces Block.forward x n_blocks
@@ -118,6 +132,47 @@ int32_t maest_block_embedding_fwd(const float* x, int32_t B, int32_t N, float* e
 
 /* fp32 -> op16 cast (weight staging). */
 int32_t maest_cast_to16(const float* src, void* dst, int64_t n, int32_t op_dtype, void* stream);
+
+/* ---- training step: Module.training_step (models/module.py:73-102) and the autograd mirrors of the forward path ---- */
+
+/* Attention backward (autograd of models/maest.py:362-375).  qkv / o / d_o op16 as in the forward; lse from the forward.
+ * delta: fp32 [B,H,N] scratch; dq32: fp32 [B*N, H*64] scratch (atomically accumulated dQ); dqkv: op16 [B*N, 3*H*64] out. */
+int32_t maest_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* dq32,
+                            void* dqkv, int32_t B, int32_t N, int32_t H, int32_t op_dtype, void* stream);
+
+/* mixup blend of a batch with a permutation of itself (models/module.py:77-86, helpers/mixup.py:5-12):
+ * out[b,:] = x[b,:]*lam[b] + x[perm[b],:]*(1-lam[b]).  x: [B, L] of x_dtype (MAEST_F16 | MAEST_F32); out fp32. */
+int32_t maest_mixup_fwd(const void* x, int32_t x_dtype, const int32_t* perm, const float* lam, float* out, int32_t B,
+                        int64_t L, void* stream);
+
+/* F.binary_cross_entropy_with_logits(logits, targets), mean over n elements (models/module.py:90).
+ * loss: fp32 scalar; dlogits[n] = (sigmoid(z) - y) / n  (the gradient for d(loss) = 1). */
+int32_t maest_bce_logits_fwd(const float* logits, const float* targets, int32_t n, float* loss, float* dlogits, void* stream);
+
+/* Backward of pooling + head ("mean" mode): final LayerNorm on rows 0/1, (cls+dist)/2, head LN + Linear
+ * (autograd of models/maest.py:806-810, :906-909).  x: saved residual stream [B,N,768]; gscale: device scalar d(loss).
+ * Writes rows 0/1 of every clip in dx [B,N,768]; accumulates the six parameter gradients; hz_ws: fp32 [B,768] scratch. */
+int32_t maest_head_bwd(const float* x, int32_t B, int32_t N, const float* dlogits, const float* gscale, const float* norm_w,
+                       const float* norm_b, const float* head_ln_w, const float* head_ln_b, const float* head_w, int32_t C,
+                       float* dx, float* hz_ws, float* d_norm_w, float* d_norm_b, float* d_head_ln_w, float* d_head_ln_b,
+                       float* d_head_w, float* d_head_b, void* stream);
+
+/* LayerNorm backward (autograd of norm1 / norm2): dx += LN'(dy); dgamma/dbeta accumulated; optional op16 copy of the updated dx. */
+int32_t maest_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                            float* dx, void* dx16, int32_t op_dtype, float* dgamma, float* dbeta, int32_t rows, void* stream);
+
+/* out[n] += sum_m in[m,n]  (bias gradients); in: [M, N] of in_dtype with row stride ld. */
+int32_t maest_colsum(const void* in, int32_t in_dtype, int64_t ld, int32_t M, int32_t N, float* out, void* stream);
+
+/* dst16[m, 0:768] = src32[remap(m), 0:768] with the row remap of maest_linear_fwd (rows_per_group = 0 -> identity); dst row stride dst_ld. */
+int32_t maest_cast_rows16(const float* src, void* dst, int64_t dst_ld, int32_t rows, int32_t rows_per_group, int32_t group_stride,
+                          int32_t row_offset, int32_t op_dtype, void* stream);
+
+/* Gradients of the token-assembly stage (autograd of models/maest.py:670-675, :785-796) from the gradient stream dx [B,N,768]:
+ * cls/dist tokens, new_pos_embed [2,768], conv bias [768], freq_new_pos_embed [768,Fp], time_new_pos_embed [768,Wt]. Accumulates. */
+int32_t maest_token_grad(const float* dx, int32_t B, int32_t N, int32_t P, int32_t Tp, int32_t Fp, int32_t Wt, int32_t t_offset,
+                         const int32_t* keep_ft, float* d_cls, float* d_dist, float* d_new_pos, float* d_conv_bias,
+                         float* d_freq, float* d_time, void* stream);
 
 #ifdef __cplusplus
 }

@@ -14,7 +14,8 @@ _inited = set()
 c_void_p, c_int32, c_int64, c_size_t, c_float = C.c_void_p, C.c_int32, C.c_int64, C.c_size_t, C.c_float
 
 F16, BF16, F32 = 0, 1, 2
-EPI_STORE16, EPI_GELU16, EPI_RESID32, EPI_STORE32 = 0, 1, 2, 3
+EPI_STORE16, EPI_GELU16, EPI_RESID32, EPI_STORE32, EPI_GELUBWD16, EPI_ATOMIC32 = 0, 1, 2, 3, 4, 5
+ABI_VERSION = 2
 HEAD_MEAN, HEAD_SEPARATED = 0, 1
 
 
@@ -37,7 +38,17 @@ SIGNATURES = {
                                       c_void_p, c_void_p]),
     "maest_linear_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32,
                                    c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
-    "maest_attention_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "maest_gemm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
+                             c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "maest_attention_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "maest_attention_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "maest_mixup_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
+    "maest_bce_logits_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
+    "maest_head_bwd": (c_int32, [c_void_p, c_int32, c_int32] + [c_void_p] * 7 + [c_int32] + [c_void_p] * 9),
+    "maest_layernorm_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
+    "maest_colsum": (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
+    "maest_cast_rows16": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
+    "maest_token_grad": (c_int32, [c_void_p] + [c_int32] * 7 + [c_void_p] * 7 + [c_void_p]),
     "maest_encoder_workspace_bytes": (c_size_t, [c_int64]),
     "maest_encoder_fwd": (c_int32, [c_void_p, c_int32, c_int32, C.POINTER(MaestBlockWeights), c_int32, c_int32, c_int32,
                                     c_int32, c_void_p, c_size_t, c_void_p]),
@@ -56,7 +67,7 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.LIB_PATH
+    path = os.environ.get("MAEST_B200_LIB") or _build.LIB_PATH
     if not os.path.exists(path):
         try:
             _build.build()

@@ -29,13 +29,19 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > t for d in deps if os.path.exists(d))
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    """Compile csrc/*.cu for sm_100a into maest_b200/lib/libmaest_b200.so; returns the path."""
-    if not force and not _stale():
+SAFE_LIB_PATH = os.path.join(LIB_DIR, "libmaest_b200_safe.so")
+
+
+def build(force: bool = False, verbose: bool = False, safe: bool = False) -> str:
+    """Compile csrc/*.cu for sm_100a into maest_b200/lib/libmaest_b200.so; returns the path.
+    safe=True builds libmaest_b200_safe.so with -DMB_SAFE_WAIT (mbarrier waits trap after 2 s instead of hanging):
+    the bring-up build for new kernels, selected at run time with MAEST_B200_LIB=<path>."""
+    out = SAFE_LIB_PATH if safe else LIB_PATH
+    if not force and not safe and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")]
-    cmd = [_nvcc(), *flags, "-o", LIB_PATH, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart"]
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + (["-DMB_SAFE_WAIT"] if safe else [])
+    cmd = [_nvcc(), *flags, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart"]
     if verbose:
         cmd.insert(1, "-Xptxas")
         cmd.insert(2, "-v")
@@ -44,7 +50,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":

@@ -7,11 +7,13 @@
 
 #include "../../include/maest_b200.h"
 #include "attention.cuh"
+#include "attention_bwd.cuh"
 #include "gemm.cuh"
 #include "logmel.cuh"
 #include "logmel_tables.h"
 #include "rowops.cuh"
 #include "tokens.cuh"
+#include "train.cuh"
 
 using namespace mb;
 
@@ -65,25 +67,37 @@ int make_tmap(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t c
   return 0;
 }
 
-template <int DT, int EPI>
+template <int DT, int EPI, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  const int num_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + GEMM_BN - 1) / GEMM_BN);
+  const int splits = p.k_splits > 1 ? p.k_splits : 1;
+  const int num_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + GEMM_BN - 1) / GEMM_BN) * splits;
   const int sms = g_num_sms[cur_device()];
   const int grid = num_tiles < sms ? num_tiles : sms;
-  gemm_tn_kernel<DT, EPI><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tn_kernel<DT, EPI, A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
 
+// the instantiated (epilogue, operand-major) combinations: forward (K,K), dgrad (K,MN), wgrad (MN,MN)
 template <int DT>
-int launch_gemm_dt(int epi, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  switch (epi) {
-    case MAEST_EPI_STORE16: return launch_gemm<DT, EPI_STORE16>(ta, tb, p, st);
-    case MAEST_EPI_GELU16: return launch_gemm<DT, EPI_GELU16>(ta, tb, p, st);
-    case MAEST_EPI_RESID32: return launch_gemm<DT, EPI_RESID32>(ta, tb, p, st);
-    case MAEST_EPI_STORE32: return launch_gemm<DT, EPI_STORE32>(ta, tb, p, st);
+int launch_gemm_dt(int epi, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn) {
+    switch (epi) {
+      case MAEST_EPI_STORE16: return launch_gemm<DT, EPI_STORE16, false, false>(ta, tb, p, st);
+      case MAEST_EPI_GELU16: return launch_gemm<DT, EPI_GELU16, false, false>(ta, tb, p, st);
+      case MAEST_EPI_RESID32: return launch_gemm<DT, EPI_RESID32, false, false>(ta, tb, p, st);
+      case MAEST_EPI_STORE32: return launch_gemm<DT, EPI_STORE32, false, false>(ta, tb, p, st);
+    }
+  } else if (!a_mn && b_mn) {
+    switch (epi) {
+      case MAEST_EPI_STORE16: return launch_gemm<DT, EPI_STORE16, false, true>(ta, tb, p, st);
+      case MAEST_EPI_STORE32: return launch_gemm<DT, EPI_STORE32, false, true>(ta, tb, p, st);
+      case MAEST_EPI_GELUBWD16: return launch_gemm<DT, EPI_GELUBWD16, false, true>(ta, tb, p, st);
+    }
+  } else if (a_mn && b_mn) {
+    if (epi == MAEST_EPI_ATOMIC32) return launch_gemm<DT, EPI_ATOMIC32, true, true>(ta, tb, p, st);
   }
-  return fail(-1, "unknown epilogue %d", epi);
+  return fail(-1, "gemm: epilogue %d is not built for operand majors (a_mn %d, b_mn %d)", epi, int(a_mn), int(b_mn));
 }
 
 template <typename K>
@@ -95,12 +109,17 @@ int set_smem(K kernel, int bytes) {
 template <int DT>
 int init_dt() {
   int r;
-  if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE16>, GEMM_SMEM_BYTES))) return r;
-  if ((r = set_smem(gemm_tn_kernel<DT, EPI_GELU16>, GEMM_SMEM_BYTES))) return r;
-  if ((r = set_smem(gemm_tn_kernel<DT, EPI_RESID32>, GEMM_SMEM_BYTES))) return r;
-  if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE32>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE16, false, false>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_GELU16, false, false>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_RESID32, false, false>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE32, false, false>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE16, false, true>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE32, false, true>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_GELUBWD16, false, true>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_ATOMIC32, true, true>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, true>, att_smem_bytes<true>()))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, false>, att_smem_bytes<false>()))) return r;
+  if ((r = set_smem(attention_bwd_kernel<DT>, ATTB_SMEM_BYTES))) return r;
   return 0;
 }
 
@@ -109,7 +128,7 @@ int init_dt() {
 extern "C" {
 
 const char* maest_last_error(void) { return g_err; }
-int32_t maest_abi_version(void) { return 1; }
+int32_t maest_abi_version(void) { return 2; }
 
 int32_t maest_init(int32_t device) {
   if (device < 0 || device >= 64) return fail(-1, "bad device %d", device);
@@ -152,26 +171,41 @@ int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_str
   return 0;
 }
 
+int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int64_t ldb, int32_t b_mn, const float* bias,
+                   int32_t M, int32_t N, int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out,
+                   const float* resid, const float* addend, int32_t rows_per_group, int32_t group_stride,
+                   int32_t row_offset, void* aux16, int32_t k_splits, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (N % 32) return fail(-1, "gemm: N %% 32 must be 0 (M %d N %d K %d)", M, N, K);   // operand alignment is checked per tensor map
+  if (op_dtype != MAEST_F16 && op_dtype != MAEST_BF16) return fail(-1, "gemm: op_dtype must be f16/bf16");
+  const int num_kb = (K + GEMM_BK - 1) / GEMM_BK;
+  if (k_splits > num_kb) k_splits = num_kb;
+  if (k_splits > 1 && epilogue != MAEST_EPI_ATOMIC32) return fail(-1, "gemm: split-K needs the ATOMIC32 epilogue");
+  CUtensorMap ta, tb;
+  int r;
+  // K-major operand: matrix [rows = M|N, cols = K]; MN-major operand: matrix [rows = K, cols = M|N]
+  if ((r = a_mn ? make_tmap(&ta, a, op_dtype, K, M, lda, 64) : make_tmap(&ta, a, op_dtype, M, K, lda, GEMM_BM))) return r;
+  if ((r = b_mn ? make_tmap(&tb, b, op_dtype, K, N, ldb, 64) : make_tmap(&tb, b, op_dtype, N, K, ldb, GEMM_BN))) return r;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = addend; p.ld_out = int(ld_out);
+  p.aux16 = aux16; p.k_splits = k_splits;
+  if (rows_per_group <= 0) { p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0; }
+  else { p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; }
+  if (epilogue == MAEST_EPI_RESID32 && !resid) return fail(-1, "gemm: RESID32 needs resid");
+  if (epilogue == MAEST_EPI_RESID32 && rows_per_group > 0) return fail(-1, "gemm: RESID32 does not support row remapping");
+  if (epilogue == MAEST_EPI_GELUBWD16 && !aux16) return fail(-1, "gemm: GELUBWD16 needs the saved pre-activation (aux16)");
+  cudaStream_t st = (cudaStream_t)stream;
+  return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st)
+                                : launch_gemm_dt<DT_F16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st);
+}
+
 int32_t maest_linear_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, int32_t M,
                          int32_t N, int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out,
                          const float* resid, const float* addend, int32_t rows_per_group, int32_t group_stride,
                          int32_t row_offset, void* stream) {
-  if (M <= 0) return 0;
-  if (N % 32 || K % 8) return fail(-1, "linear: N %% 32 and K %% 8 must be 0 (N %d K %d)", N, K);
-  if (op_dtype != MAEST_F16 && op_dtype != MAEST_BF16) return fail(-1, "linear: op_dtype must be f16/bf16");
-  CUtensorMap ta, tb;
-  int r;
-  if ((r = make_tmap(&ta, a, op_dtype, M, K, lda, GEMM_BM))) return r;
-  if ((r = make_tmap(&tb, w, op_dtype, N, K, ldw, GEMM_BN))) return r;
-  GemmParams p;
-  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = addend; p.ld_out = int(ld_out);
-  if (rows_per_group <= 0) { p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0; }
-  else { p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; }
-  if (epilogue == MAEST_EPI_RESID32 && !resid) return fail(-1, "linear: RESID32 needs resid");
-  if (epilogue == MAEST_EPI_RESID32 && rows_per_group > 0) return fail(-1, "linear: RESID32 does not support row remapping");
-  cudaStream_t st = (cudaStream_t)stream;
-  return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, ta, tb, p, st)
-                                : launch_gemm_dt<DT_F16>(epilogue, ta, tb, p, st);
+  if (epilogue < MAEST_EPI_STORE16 || epilogue > MAEST_EPI_STORE32) return fail(-1, "linear: unknown epilogue %d", epilogue);
+  return maest_gemm(a, lda, 0, w, ldw, 0, bias, M, N, K, op_dtype, epilogue, out, ld_out, resid, addend, rows_per_group,
+                    group_stride, row_offset, nullptr, 1, stream);
 }
 
 int32_t maest_layernorm_fwd(const float* x, const float* w, const float* b, void* y16, int32_t op_dtype, int32_t rows,
@@ -186,7 +220,7 @@ int32_t maest_layernorm_fwd(const float* x, const float* w, const float* b, void
   return 0;
 }
 
-int32_t maest_attention_fwd(const void* qkv, void* out, int32_t B, int32_t N, int32_t H, int32_t op_dtype,
+int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t op_dtype,
                             int32_t variant, void* stream) {
   if (B <= 0 || N <= 0) return 0;
   CUtensorMap tq;
@@ -195,6 +229,7 @@ int32_t maest_attention_fwd(const void* qkv, void* out, int32_t B, int32_t N, in
   AttnParams p;
   p.B = B; p.N = N; p.H = H; p.ld_qkv = 3 * H * ATT_D; p.ld_out = H * ATT_D; p.out = out;
   p.scale_log2 = 0.125f * 1.4426950408889634f;
+  p.lse = lse;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, H, B);
   cudaStream_t st = (cudaStream_t)stream;
   if (op_dtype == MAEST_BF16) {
@@ -274,7 +309,7 @@ int32_t maest_encoder_fwd(float* x, int32_t B, int32_t N, const MaestBlockWeight
     if ((r = maest_layernorm_fwd(x, w.ln1_w, w.ln1_b, h16, op_dtype, int(M), 1e-6f, nullptr, nullptr, stream))) return r;
     if ((r = maest_linear_fwd(h16, 768, w.qkv_w, 768, w.qkv_b, int(M), 2304, 768, op_dtype, MAEST_EPI_STORE16, qkv16, 2304,
                               nullptr, nullptr, 0, 0, 0, stream))) return r;
-    if ((r = maest_attention_fwd(qkv16, o16, B, N, 12, op_dtype, attn_variant, stream))) return r;
+    if ((r = maest_attention_fwd(qkv16, o16, nullptr, B, N, 12, op_dtype, attn_variant, stream))) return r;
     if (attn_only) {
       return maest_linear_fwd(o16, 768, w.proj_w, 768, w.proj_b, int(M), 768, 768, op_dtype, MAEST_EPI_STORE32, x, 768, nullptr,
                               nullptr, 0, 0, 0, stream);
@@ -320,6 +355,124 @@ int32_t maest_cast_to16(const float* src, void* dst, int64_t n, int32_t op_dtype
   if (op_dtype == MAEST_BF16) cast_to16_kernel<DT_BF16><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
   else if (op_dtype == MAEST_F16) cast_to16_kernel<DT_F16><<<blocks, 256, 0, (cudaStream_t)stream>>>(src, dst, n);
   else return fail(-1, "cast: op_dtype must be f16/bf16");
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------ training step
+int32_t maest_attention_bwd(const void* qkv, const void* o, const void* d_o, const float* lse, float* delta, float* dq32,
+                            void* dqkv, int32_t B, int32_t N, int32_t H, int32_t op_dtype, void* stream) {
+  if (B <= 0 || N <= 0) return 0;
+  if (H != 12) return fail(-1, "attention_bwd: H must be 12");
+  cudaStream_t st = (cudaStream_t)stream;
+  const long M = long(B) * N;
+  CUtensorMap tq, td;
+  int r;
+  if ((r = make_tmap(&tq, qkv, op_dtype, M, 3 * H * 64, 3 * H * 64, 128))) return r;
+  if ((r = make_tmap(&td, d_o, op_dtype, M, H * 64, H * 64, 128))) return r;
+  CUDA_OK(cudaMemsetAsync(dq32, 0, size_t(M) * H * 64 * sizeof(float), st));
+  AttnBwdParams p;
+  p.B = B; p.N = N; p.H = H; p.lse = lse; p.delta = delta; p.dq32 = dq32; p.dqkv16 = dqkv;
+  p.scale = 0.125f; p.scale_log2 = 0.125f * 1.4426950408889634f;
+  const long nd = M * H;
+  dim3 grid((N + 127) / 128, H, B);
+  const int cast_blocks = int((M + 7) / 8);
+  if (op_dtype == MAEST_BF16) {
+    attn_delta_kernel<DT_BF16><<<unsigned((nd + 255) / 256), 256, 0, st>>>(o, d_o, delta, B, N, H);
+    attention_bwd_kernel<DT_BF16><<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, st>>>(tq, td, p);
+    cast_rows16_kernel<DT_BF16><<<cast_blocks, 256, 0, st>>>(dq32, dqkv, 3 * H * 64, int(M), 0x7fffffff, 0, 0);
+  } else if (op_dtype == MAEST_F16) {
+    attn_delta_kernel<DT_F16><<<unsigned((nd + 255) / 256), 256, 0, st>>>(o, d_o, delta, B, N, H);
+    attention_bwd_kernel<DT_F16><<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, st>>>(tq, td, p);
+    cast_rows16_kernel<DT_F16><<<cast_blocks, 256, 0, st>>>(dq32, dqkv, 3 * H * 64, int(M), 0x7fffffff, 0, 0);
+  } else return fail(-1, "attention_bwd: op_dtype must be f16/bf16");
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_mixup_fwd(const void* x, int32_t x_dtype, const int32_t* perm, const float* lam, float* out, int32_t B,
+                        int64_t L, void* stream) {
+  if (B <= 0 || L <= 0) return 0;
+  dim3 grid(unsigned(L / 256 / 8 + 1 > 1024 ? 1024 : L / 256 / 8 + 1), B);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (x_dtype == MAEST_F16) mixup_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(x), perm, lam, out, B, L);
+  else if (x_dtype == MAEST_F32) mixup_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(x), perm, lam, out, B, L);
+  else return fail(-1, "mixup: input must be f16 or f32");
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_bce_logits_fwd(const float* logits, const float* targets, int32_t n, float* loss, float* dlogits, void* stream) {
+  if (n <= 0) return fail(-1, "bce: empty input");
+  bce_logits_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(logits, targets, loss, dlogits, n);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_head_bwd(const float* x, int32_t B, int32_t N, const float* dlogits, const float* gscale, const float* norm_w,
+                       const float* norm_b, const float* head_ln_w, const float* head_ln_b, const float* head_w, int32_t C,
+                       float* dx, float* hz_ws, float* d_norm_w, float* d_norm_b, float* d_head_ln_w, float* d_head_ln_b,
+                       float* d_head_w, float* d_head_b, void* stream) {
+  if (B <= 0) return 0;
+  if (C > 1024) return fail(-1, "head_bwd: at most 1024 classes");
+  HeadBwdParams p;
+  p.x = x; p.N = N; p.dlogits = dlogits; p.gscale = gscale; p.norm_w = norm_w; p.norm_b = norm_b; p.hln_w = head_ln_w;
+  p.hln_b = head_ln_b; p.head_w = head_w; p.C = C; p.dx = dx; p.hz = hz_ws; p.d_norm_w = d_norm_w; p.d_norm_b = d_norm_b;
+  p.d_hln_w = d_head_ln_w; p.d_hln_b = d_head_ln_b;
+  cudaStream_t st = (cudaStream_t)stream;
+  head_bwd_clip_kernel<<<B, 256, 0, st>>>(p);
+  head_wgrad_kernel<<<C, 256, 0, st>>>(dlogits, gscale, hz_ws, B, C, d_head_w, d_head_b);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
+                            float* dx, void* dx16, int32_t op_dtype, float* dgamma, float* dbeta, int32_t rows, void* stream) {
+  if (rows <= 0) return 0;
+  const int sms = g_num_sms[cur_device()] > 0 ? g_num_sms[cur_device()] : 148;
+  int blocks = (rows + 7) / 8;
+  if (blocks > sms * 4) blocks = sms * 4;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op_dtype == MAEST_BF16) layernorm_bwd_kernel<DT_BF16><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, dx16, dgamma, dbeta, rows);
+  else if (op_dtype == MAEST_F16) layernorm_bwd_kernel<DT_F16><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, dx16, dgamma, dbeta, rows);
+  else return fail(-1, "layernorm_bwd: op_dtype must be f16/bf16");
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_colsum(const void* in, int32_t in_dtype, int64_t ld, int32_t M, int32_t N, float* out, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  dim3 grid((N + 255) / 256, M < 128 ? M : 128);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (in_dtype == MAEST_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), ld, M, N, out);
+  else if (in_dtype == MAEST_F16) colsum_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(in), ld, M, N, out);
+  else if (in_dtype == MAEST_BF16) colsum_kernel<__nv_bfloat16><<<grid, 256, 0, st>>>(reinterpret_cast<const __nv_bfloat16*>(in), ld, M, N, out);
+  else return fail(-1, "colsum: bad dtype");
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_cast_rows16(const float* src, void* dst, int64_t dst_ld, int32_t rows, int32_t rows_per_group, int32_t group_stride,
+                          int32_t row_offset, int32_t op_dtype, void* stream) {
+  if (rows <= 0) return 0;
+  if (rows_per_group <= 0) { rows_per_group = 0x7fffffff; group_stride = 0; row_offset = 0; }
+  const int blocks = (rows + 7) / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op_dtype == MAEST_BF16) cast_rows16_kernel<DT_BF16><<<blocks, 256, 0, st>>>(src, dst, dst_ld, rows, rows_per_group, group_stride, row_offset);
+  else if (op_dtype == MAEST_F16) cast_rows16_kernel<DT_F16><<<blocks, 256, 0, st>>>(src, dst, dst_ld, rows, rows_per_group, group_stride, row_offset);
+  else return fail(-1, "cast_rows16: op_dtype must be f16/bf16");
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_token_grad(const float* dx, int32_t B, int32_t N, int32_t P, int32_t Tp, int32_t Fp, int32_t Wt, int32_t t_offset,
+                         const int32_t* keep_ft, float* d_cls, float* d_dist, float* d_new_pos, float* d_conv_bias,
+                         float* d_freq, float* d_time, void* stream) {
+  if (B <= 0) return 0;
+  TokenGradParams p;
+  p.dx = dx; p.B = B; p.N = N; p.P = P; p.Tp = Tp; p.Fp = Fp; p.Wt = Wt; p.t_off = t_offset; p.keep_ft = keep_ft;
+  p.d_cls = d_cls; p.d_dist = d_dist; p.d_new_pos = d_new_pos; p.d_conv_bias = d_conv_bias; p.d_freq = d_freq; p.d_time = d_time;
+  token_grad_kernel<<<2 + P, 256, 0, (cudaStream_t)stream>>>(p);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -39,6 +39,7 @@ struct AttnParams {
   int ld_out;       // H*64
   void* out;        // [B*N, H*64] 16-bit
   float scale_log2; // d^-0.5 * log2(e)
+  float* lse;       // optional [B, H, N] fp32: m + log2(l) per query row in the scaled log2 domain (saved for backward)
 };
 
 __device__ __forceinline__ float ex2_approx(float x) {
@@ -195,23 +196,30 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
       tc_fence_before();
       mbar_arrive(s_free);
       float mt = -INFINITY;
-      if (full_tile) {
+      if (!full_tile) {
 #pragma unroll
-        for (int i = 0; i < 128; ++i) mt = fmaxf(mt, __uint_as_float(s[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 128; ++i) {
+        for (int i = 0; i < 128; ++i)
           if (i >= valid) s[i] = 0xff800000u;   // -inf: masked keys contribute exp2(-inf) = 0
-          mt = fmaxf(mt, __uint_as_float(s[i]));
+      }
+      {
+        float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;   // four independent chains
+#pragma unroll
+        for (int i = 0; i < 128; i += 4) {
+          m0 = fmaxf(m0, __uint_as_float(s[i]));
+          m1 = fmaxf(m1, __uint_as_float(s[i + 1]));
+          m2 = fmaxf(m2, __uint_as_float(s[i + 2]));
+          m3 = fmaxf(m3, __uint_as_float(s[i + 3]));
         }
+        mt = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
       }
       const float mt_sc = mt * sc;
+      bool waited_pv = (j == 0);   // PV_{j-1} must retire before O is corrected or P is overwritten
       if (j > 0) {
-        // PV_{j-1} must be complete before O is corrected or P is overwritten
-        mbar_wait(o_done, (j - 1) & 1);
-        tc_fence_after();
         const bool need = mt_sc > m_run + 8.0f;   // lazy rescale: p stays <= 2^8 against a stale max
         if (__any_sync(0xffffffffu, need)) {
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
+          waited_pv = true;
           float f = 1.0f;
           if (need) {
             f = ex2_approx(m_run - mt_sc);
@@ -232,7 +240,8 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
       } else {
         m_run = mt_sc;
       }
-      // p = exp2(s*sc - m), row sum, P -> 16-bit
+      // p = exp2(s*sc - m), row sum, P -> 16-bit.  The first 32 exponentials are computed BEFORE waiting for
+      // PV_{j-1}, so the tensor-pipe latency of the previous tile hides behind MUFU work.
       const float neg_m = -m_run;
       float l0 = 0.f, l1 = 0.f;
 #pragma unroll
@@ -245,6 +254,10 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
           l0 += p0;
           l1 += p1;
           pk[i >> 1] = O16::pack(p0, p1);
+        }
+        if (c == 0 && !waited_pv) {
+          mbar_wait(o_done, (j - 1) & 1);
+          tc_fence_after();
         }
         if constexpr (P_IN_TMEM) {
           tmem_st16(tP + lane_off + uint32_t(c * 16), pk);
@@ -270,6 +283,7 @@ attention_fwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnPar
     tc_fence_after();
     const float inv_l = 1.0f / l_run;
     const int qrow = q0 + row;
+    if (p.lse != nullptr && qrow < p.N) p.lse[(long(b) * p.H + h) * p.N + qrow] = m_run + log2f(l_run);
     typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.out) + long(row_base + qrow) * p.ld_out + h * ATT_D;
 #pragma unroll 1
     for (int c = 0; c < 2; ++c) {

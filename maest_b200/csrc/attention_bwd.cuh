@@ -1,0 +1,241 @@
+// Flash-style attention BACKWARD for sm_100a (autograd of models/maest.py:362-375), d_head = 64.
+//
+// CTA = one 128-key tile of one (clip, head); it keeps K_j, V_j resident, streams the query tiles (Q_i, dO_i) and
+// accumulates dK_j, dV_j in TMEM.  Per (i, j) five tcgen05 GEMMs:
+//     S  = Q_i K_j^T            dP = dO_i V_j^T                       (128x128x64 each, fp32 in TMEM)
+//     dV += P^T dO_i            dK += dS^T Q_i        dQ_i = dS K_j    (128x64x128 each)
+// with  P = exp2(S*c - lse),  dS = P * (dP - delta) * scale  computed by 128 threads (one query row each) and
+// written as 16-bit tiles to shared memory in the SWIZZLE_128B layout, where the same bytes serve as a K-major
+// A operand (dQ) and as an MN-major A operand (dV, dK).  Q, K, dO are consumed in their natural [row][d] layout
+// (K-major for S / dP, MN-major B for dK / dQ / dV) — no transposes are materialised anywhere.
+// dQ tiles are reduced across key tiles with fp32 atomics into dq32; dK/dV are written once as 16-bit.
+#pragma once
+#include "attention.cuh"
+
+namespace mb {
+
+constexpr int ATTB_THREADS = 192;
+constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 10 + 128;   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves)
+
+struct AttnBwdParams {
+  int B, N, H;
+  const float* lse;     // [B, H, N]
+  const float* delta;   // [B, H, N]
+  float* dq32;          // [B*N, H*64] fp32, zero-initialised by the caller (atomically accumulated)
+  void* dqkv16;         // [B*N, 3*H*64] 16-bit: the k and v column blocks are written here
+  float scale_log2, scale;
+};
+
+template <int DT>
+__global__ void __launch_bounds__(ATTB_THREADS, 1)
+attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
+                     const AttnBwdParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  using O16 = Op16<DT>;
+  uint8_t* sK = smem;
+  uint8_t* sV = smem + ATT_TILE_BYTES;
+  uint8_t* sQ = smem + 2 * ATT_TILE_BYTES;    // [2]
+  uint8_t* sdO = smem + 4 * ATT_TILE_BYTES;   // [2]
+  uint8_t* sP = smem + 6 * ATT_TILE_BYTES;    // two [128 q x 64 keys] halves
+  uint8_t* sdS = smem + 8 * ATT_TILE_BYTES;   // two halves
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATTB_SMEM_BYTES - 128);
+  uint64_t* kv_full = bars;          // 1
+  uint64_t* qdo_full = bars + 1;     // [2]
+  uint64_t* qdo_empty = bars + 3;    // [2]
+  uint64_t* sdp_full = bars + 5;     // S_i, dP_i in TMEM
+  uint64_t* pds_full = bars + 6;     // P_i, dS_i in smem (count 128)
+  uint64_t* mma2_done = bars + 7;    // dV/dK/dQ GEMMs of iteration i retired
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int kv0 = blockIdx.x * 128;
+  const int h = blockIdx.y, b = blockIdx.z;
+  const int row_base = b * p.N;
+  const int nq = (p.N + 127) / 128;
+
+  if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
+    printf("attention_bwd: dynamic smem base not 1024-aligned\n");
+    __trap();
+  }
+  if (warp == 5 && lane == 0) {
+    mbar_init(kv_full, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    mbar_init(sdp_full, 1);
+    mbar_init(pds_full, 128);
+    mbar_init(mma2_done, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) {
+    if (lane == 0) { tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do); }
+    tmem_alloc<512>(tmem_slot);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
+      tma_load_2d(sK, &tmap_qkv, kv_full, p.H * 64 + h * 64, row_base + kv0);
+      tma_load_2d(sV, &tmap_qkv, kv_full, 2 * p.H * 64 + h * 64, row_base + kv0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(&qdo_empty[stage], phase ^ 1);
+        mbar_expect_tx(&qdo_full[stage], 2 * ATT_TILE_BYTES);
+        tma_load_2d(sQ + stage * ATT_TILE_BYTES, &tmap_qkv, &qdo_full[stage], h * 64, row_base + i * 128);
+        tma_load_2d(sdO + stage * ATT_TILE_BYTES, &tmap_do, &qdo_full[stage], h * 64, row_base + i * 128);
+        if (++stage == 2) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(DT, 128, 128, 0, 0);    // S, dP: A K-major, B K-major
+      constexpr uint32_t idesc_t = make_idesc(DT, 128, 64, 1, 1);     // dV, dK: A = P^T / dS^T (MN-major), B MN-major
+      constexpr uint32_t idesc_q = make_idesc(DT, 128, 64, 0, 1);     // dQ: A = dS (K-major), B = K (MN-major)
+      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sdS);
+      auto issue_s_dp = [&](int stage) {
+        const uint64_t qd = make_sdesc(smem_u32(sQ + stage * ATT_TILE_BYTES), 16, 1024);
+        const uint64_t od = make_sdesc(smem_u32(sdO + stage * ATT_TILE_BYTES), 16, 1024);
+        const uint64_t kd = make_sdesc(aK, 16, 1024), vd = make_sdesc(aV, 16, 1024);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(tS, qd + uint64_t(2 * k), kd + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(tdP, od + uint64_t(2 * k), vd + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
+        tc_commit(sdp_full);
+      };
+      mbar_wait(kv_full, 0);
+      mbar_wait(&qdo_full[0], 0);
+      tc_fence_after();
+      issue_s_dp(0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nq; ++i) {
+        int nstage = stage ^ 1;
+        uint32_t nphase = stage == 1 ? phase ^ 1 : phase;
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
+        if (i + 1 < nq) {
+          mbar_wait(&qdo_full[nstage], nphase);
+          tc_fence_after();
+          issue_s_dp(nstage);
+        }
+        const uint32_t aQ = smem_u32(sQ + stage * ATT_TILE_BYTES), aO = smem_u32(sdO + stage * ATT_TILE_BYTES);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dV[key, d] += sum_q P[q, key] dO[q, d]
+          mma_ss(tdV, make_sdesc(aP + uint32_t(k * 2048), 16384, 1024), make_sdesc(aO + uint32_t(k * 2048), 8192, 1024), idesc_t,
+                 (i | k) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dK[key, d] += sum_q dS[q, key] Q[q, d]
+          mma_ss(tdK, make_sdesc(aDS + uint32_t(k * 2048), 16384, 1024), make_sdesc(aQ + uint32_t(k * 2048), 8192, 1024), idesc_t,
+                 (i | k) ? 1u : 0u);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)   // dQ[q, d] = sum_key dS[q, key] K[key, d]
+          mma_ss(tdQ, make_sdesc(aDS + uint32_t((k >> 2) * ATT_TILE_BYTES), 16, 1024) + uint64_t(2 * (k & 3)),
+                 make_sdesc(aK + uint32_t(k * 2048), 8192, 1024), idesc_q, k ? 1u : 0u);
+        tc_commit(&qdo_empty[stage]);
+        tc_commit(mma2_done);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else {
+    const int row = warp * 32 + lane;
+    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    const float sc = p.scale_log2, scale = p.scale;
+    const long stat_base = (long(b) * p.H + h) * p.N;
+    auto drain_dq = [&](int i) {   // dQ_i: TMEM -> fp32 atomics
+      const int qrow = i * 128 + row;
+      float* dst = p.dq32 + long(row_base + qrow) * (p.H * 64) + h * 64;
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tdQ + lane_off + uint32_t(c * 32), v);
+        tc_wait_ld();
+        if (qrow < p.N) {
+#pragma unroll
+          for (int k = 0; k < 32; ++k) atomicAdd(dst + c * 32 + k, __uint_as_float(v[k]));
+        }
+      }
+    };
+    for (int i = 0; i < nq; ++i) {
+      const int qrow = i * 128 + row;
+      const bool q_ok = qrow < p.N;
+      const float lse2 = q_ok ? p.lse[stat_base + qrow] : 0.f;
+      const float dlt = q_ok ? p.delta[stat_base + qrow] : 0.f;
+      mbar_wait(sdp_full, i & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        uint32_t sv[32], dv[32];
+        tmem_ld32(tS + lane_off + uint32_t(c * 32), sv);
+        tmem_ld32(tdP + lane_off + uint32_t(c * 32), dv);
+        tc_wait_ld();
+        uint32_t pkP[16], pkD[16];
+#pragma unroll
+        for (int k = 0; k < 32; k += 2) {
+          const int key = kv0 + c * 32 + k;
+          float p0 = ex2_approx(fmaf(__uint_as_float(sv[k]), sc, -lse2));
+          float p1 = ex2_approx(fmaf(__uint_as_float(sv[k + 1]), sc, -lse2));
+          if (!q_ok || key >= p.N) p0 = 0.f;
+          if (!q_ok || key + 1 >= p.N) p1 = 0.f;
+          const float d0 = p0 * (__uint_as_float(dv[k]) - dlt) * scale;
+          const float d1 = p1 * (__uint_as_float(dv[k + 1]) - dlt) * scale;
+          pkP[k >> 1] = O16::pack(p0, p1);
+          pkD[k >> 1] = O16::pack(d0, d1);
+        }
+        if (c == 0 && i > 0) {   // the previous iteration's GEMMs must retire before P/dS smem is overwritten
+          mbar_wait(mma2_done, (i - 1) & 1);
+          tc_fence_after();
+          drain_dq(i - 1);
+        }
+        uint8_t* bp = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
+        uint8_t* bd = sdS + (c >> 1) * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          const int chunk = (((c & 1) * 4 + q4) ^ (row & 7)) * 16;
+          *reinterpret_cast<uint4*>(bp + chunk) = make_uint4(pkP[4 * q4], pkP[4 * q4 + 1], pkP[4 * q4 + 2], pkP[4 * q4 + 3]);
+          *reinterpret_cast<uint4*>(bd + chunk) = make_uint4(pkD[4 * q4], pkD[4 * q4 + 1], pkD[4 * q4 + 2], pkD[4 * q4 + 3]);
+        }
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      mbar_arrive(pds_full);
+    }
+    mbar_wait(mma2_done, (nq - 1) & 1);
+    tc_fence_after();
+    drain_dq(nq - 1);
+    // dK_j, dV_j -> 16-bit column blocks of dqkv
+    const int key = kv0 + row;
+    typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.dqkv16) + long(row_base + key) * (3 * p.H * 64) + h * 64;
+#pragma unroll 1
+    for (int which = 0; which < 2; ++which) {   // 0: dK -> column block 1, 1: dV -> column block 2
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) {
+        uint32_t v[32];
+        tmem_ld32((which ? tdV : tdK) + lane_off + uint32_t(c * 32), v);
+        tc_wait_ld();
+        if (key < p.N) {
+          typename O16::T* d = dst + (which + 1) * p.H * 64 + c * 32;
+#pragma unroll
+          for (int k = 0; k < 32; k += 8)
+            st_global_v4(d + k, O16::pack(__uint_as_float(v[k]), __uint_as_float(v[k + 1])),
+                         O16::pack(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
+                         O16::pack(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])),
+                         O16::pack(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+}
+
+}  // namespace mb

@@ -31,6 +31,8 @@ enum : int {
   EPI_GELU16 = 1,   // out16[r,n] = gelu_erf(acc + bias[n])
   EPI_RESID32 = 2,  // out32[r,n] = resid32[r,n] + acc + bias[n]        (out32 may alias resid32)
   EPI_STORE32 = 3,  // out32[r,n] = acc + bias[n] + addend[(m % rows_per_group), n]
+  EPI_GELUBWD16 = 4,  // out16[r,n] = acc * gelu'(aux16[r,n])                (fc2 dgrad fused with the GELU backward)
+  EPI_ATOMIC32 = 5,   // out32[r,n] += acc  (red.global.add.f32; split-K weight gradients accumulate into .grad)
 };
 
 struct GemmParams {
@@ -39,7 +41,10 @@ struct GemmParams {
   void* out;             // 16-bit or fp32, row stride ld_out elements
   const float* resid;    // EPI_RESID32
   const float* addend;   // EPI_STORE32: optional [rows_per_group, N] table (pos-embed), else null
+  void* aux16;           // EPI_GELU16: optional second output, the pre-activation (saved for backward);
+                         // EPI_GELUBWD16: input, the saved pre-activation.  Same shape / row stride as out.
   int ld_out;
+  int k_splits;          // >1: the K loop is split across CTAs (use with EPI_ATOMIC32)
   // output row remap:  r = (m / rows_per_group) * group_stride + row_offset + (m % rows_per_group)
   int rows_per_group, group_stride, row_offset;
 };
@@ -71,7 +76,24 @@ __device__ __forceinline__ float gelu_erf_fast(float x) {
   return fmaf(hx, erf_v, hx);
 }
 
-template <int DT, int EPI>
+// d/dx [x Phi(x)] = Phi(x) + x phi(x), same erf approximation as the forward
+__device__ __forceinline__ float gelu_erf_grad_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));
+  float p = fmaf(1.061405429f, t, -1.453152027f);
+  p = fmaf(p, t, 1.421413741f);
+  p = fmaf(p, t, -0.284496736f);
+  p = fmaf(p, t, 0.254829592f);
+  p *= t;
+  const float e = ex2_approx_ftz(-1.4426950408889634f * z * z);   // exp(-x^2 / 2)
+  const float erf_v = copysignf(fmaf(-p, e, 1.0f), x);
+  return fmaf(0.5f, erf_v, 0.5f) + x * e * 0.3989422804014327f;
+}
+
+// A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous and the reduction index as the row
+// ("MN-major": natural layout of activations / gradients / weights in the backward GEMMs, so no transposes are
+// materialised).  Such a tile is fetched as [64 k-rows x 64 elements] TMA boxes, one per 64-wide M/N group.
+template <int DT, int EPI, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                const GemmParams p) {
@@ -89,8 +111,14 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
   const int lane = threadIdx.x & 31;
   const int num_m = (p.M + GEMM_BM - 1) / GEMM_BM;
   const int num_n = (p.N + GEMM_BN - 1) / GEMM_BN;
-  const int num_tiles = num_m * num_n;
-  const int num_kb = (p.K + GEMM_BK - 1) / GEMM_BK;
+  const int splits = p.k_splits > 1 ? p.k_splits : 1;
+  const int num_tiles = num_m * num_n * splits;       // work items: (output tile, K split)
+  const int num_kb_total = (p.K + GEMM_BK - 1) / GEMM_BK;
+  auto kb_range = [&](int t, int& kb0, int& kb1) {
+    const int sp = t % splits;
+    kb0 = int(long(num_kb_total) * sp / splits);
+    kb1 = int(long(num_kb_total) * (sp + 1) / splits);
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmap_a);
@@ -118,22 +146,35 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       int stage = 0;
       uint32_t phase = 0;
       for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-        const int m0 = (t / num_n) * GEMM_BM;
-        const int n0 = (t % num_n) * GEMM_BN;
-        for (int kb = 0; kb < num_kb; ++kb) {
+        const int tile = t / splits;
+        const int m0 = (tile / num_n) * GEMM_BM;
+        const int n0 = (tile % num_n) * GEMM_BN;
+        int kb0, kb1;
+        kb_range(t, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * GEMM_STAGE_BYTES;
           uint8_t* sb = sa + GEMM_A_BYTES;
           mbar_expect_tx(&full_bar[stage], GEMM_STAGE_BYTES);
-          tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
-          tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+          if constexpr (A_MN) {
+#pragma unroll
+            for (int g = 0; g < GEMM_BM / 64; ++g) tma_load_2d(sa + g * 8192, &tmap_a, &full_bar[stage], m0 + g * 64, kb * GEMM_BK);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full_bar[stage], kb * GEMM_BK, m0);
+          }
+          if constexpr (B_MN) {
+#pragma unroll
+            for (int g = 0; g < GEMM_BN / 64; ++g) tma_load_2d(sb + g * 8192, &tmap_b, &full_bar[stage], n0 + g * 64, kb * GEMM_BK);
+          } else {
+            tma_load_2d(sb, &tmap_b, &full_bar[stage], kb * GEMM_BK, n0);
+          }
           if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(DT, GEMM_BM, GEMM_BN, 0, 0);
+      constexpr uint32_t idesc = make_idesc(DT, GEMM_BM, GEMM_BN, A_MN ? 1 : 0, B_MN ? 1 : 0);
       int stage = 0;
       uint32_t phase = 0;
       int as = 0;
@@ -142,16 +183,20 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
         mbar_wait(&tempty_bar[as], aphase ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + uint32_t(as * GEMM_BN);
-        for (int kb = 0; kb < num_kb; ++kb) {
+        int kb0, kb1;
+        kb_range(t, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * GEMM_STAGE_BYTES);
-          const uint64_t adesc = make_sdesc(sa, 16, 1024);
-          const uint64_t bdesc = make_sdesc(sa + GEMM_A_BYTES, 16, 1024);
+          const uint32_t sb = sa + GEMM_A_BYTES;
 #pragma unroll
           for (int k = 0; k < GEMM_BK / 16; ++k) {
-            // advance 16 K-elements = 32 bytes inside the 128-byte swizzle row: +2 in the (addr >> 4) field
-            mma_ss(d_tmem, adesc + uint64_t(2 * k), bdesc + uint64_t(2 * k), idesc, (kb | k) ? 1u : 0u);
+            // K-major: advance 16 K-elements = 32 bytes inside the 128-byte swizzle row.
+            // MN-major: advance 16 k-rows = 2048 bytes; LBO = 8192 (next 64-wide M/N group), SBO = 1024 (next 8 k-rows).
+            const uint64_t adesc = A_MN ? make_sdesc(sa + uint32_t(k * 2048), 8192, 1024) : make_sdesc(sa, 16, 1024) + uint64_t(2 * k);
+            const uint64_t bdesc = B_MN ? make_sdesc(sb + uint32_t(k * 2048), 8192, 1024) : make_sdesc(sb, 16, 1024) + uint64_t(2 * k);
+            mma_ss(d_tmem, adesc, bdesc, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           tc_commit(&empty_bar[stage]);
           if (++stage == GEMM_STAGES) { stage = 0; phase ^= 1; }
@@ -172,8 +217,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-      const int m0 = (t / num_n) * GEMM_BM + q * 32;
-      const int n0 = (t % num_n) * GEMM_BN + half * 128;
+      const int tile = t / splits;
+      const int m0 = (tile / num_n) * GEMM_BM + q * 32;
+      const int n0 = (tile % num_n) * GEMM_BN + half * 128;
       int nchunks = (p.N - n0 + 31) / 32;
       nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN + half * 128);
@@ -238,14 +284,29 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           int pr = 0;
           if (identity_rows) { r = m; }
           else { pr = m % p.rows_per_group; r = long(m / p.rows_per_group) * p.group_stride + p.row_offset + pr; }
-          if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16) {
+          if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELUBWD16) {
             if constexpr (EPI == EPI_GELU16) {
+              if (p.aux16 != nullptr) {   // training: keep the pre-activation for the backward pass
+                uint2 pre;
+                pre.x = O::pack(a.x, a.y);
+                pre.y = O::pack(a.z, a.w);
+                *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.aux16) + r * p.ld_out + col) = pre;
+              }
               a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
+            }
+            if constexpr (EPI == EPI_GELUBWD16) {
+              const uint2 pre = *reinterpret_cast<const uint2*>(reinterpret_cast<const typename O::T*>(p.aux16) + r * p.ld_out + col);
+              const float2 u01 = O::unpack(pre.x), u23 = O::unpack(pre.y);
+              a.x *= gelu_erf_grad_fast(u01.x); a.y *= gelu_erf_grad_fast(u01.y);
+              a.z *= gelu_erf_grad_fast(u23.x); a.w *= gelu_erf_grad_fast(u23.y);
             }
             uint2 o;
             o.x = O::pack(a.x, a.y);
             o.y = O::pack(a.z, a.w);
             *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.out) + r * p.ld_out + col) = o;
+          } else if constexpr (EPI == EPI_ATOMIC32) {
+            float* dst = reinterpret_cast<float*>(p.out) + r * p.ld_out + col;
+            atomicAdd(dst, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
           } else if constexpr (EPI == EPI_RESID32) {
             *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
           } else {

@@ -45,3 +45,72 @@ def my_mixup(size, alpha):
     lambd = np.random.beta(alpha, alpha, size).astype(np.float32)
     lambd = np.concatenate([lambd[:, None], 1 - lambd[:, None]], 1).max(1)
     return rn_indices, torch.FloatTensor(lambd)
+
+
+class Module(_LightningModule):
+    """Drop-in for the reference's Lightning `Module` (models/module.py:44-276) for the hot path: `net`, `training_step`,
+    `forward`, `predict_step`, `configure_optimizers`.  Validation metrics / SWA plumbing stay Lightning's business."""
+
+    @module_ing.capture
+    def __init__(self, do_swa=True, swa_epoch_start=50, swa_lrs=2e-5, swa_freq=5, mixup_alpha=0.3, distributed_mode=False,
+                 optimizer=None, net=None):
+        super().__init__()
+        self.mixup_alpha = mixup_alpha
+        self.do_swa = do_swa
+        self.swa_freq = swa_freq
+        self.swa_epoch_start = swa_epoch_start
+        self.swa_lrs = swa_lrs
+        self.distributed_mode = distributed_mode
+        self.optimizer_cfg = dict(MODULE_DEFAULT_CONF["optimizer"], **(optimizer or {}))
+        self.net = net if net is not None else get_maest()      # models/module.py:63 (arguments come from the Sacred ingredient)
+        self.validation_outputs = []
+        self.test_outputs = []
+        self.transformer_block = -1
+
+    def forward(self, batch, transformer_block=-1):
+        # the reference ignores `transformer_block` here and always passes -1 (models/module.py:68-71); kept as is
+        return self.net.forward(batch, transformer_block=-1, return_self_attention=False)
+
+    def training_step(self, batch, batch_idx):
+        from .train import training_forward
+        x, f, y = batch
+        mix = None
+        if self.mixup_alpha > 0:
+            mix = my_mixup(len(y), self.mixup_alpha)             # host RNG: torch.randperm, then np.random.beta
+        loss, _ = training_forward(self.net, x, y, mix)
+        self.log("train_loss", loss, on_step=True, on_epoch=True, prog_bar=True, logger=True, batch_size=len(y), sync_dist=True)
+        return loss
+
+    def predict_step(self, batch, batch_idx: int, dataloader_idx: int = None):
+        x, f, y = batch
+        logits, embed = self.forward(x, transformer_block=self.transformer_block)
+        return {"logits": logits.detach().cpu(), "embeddings": embed.detach().cpu(), "filename": f}
+
+    def set_prediction_tranformer_block(self, transformer_block):
+        self.transformer_block = transformer_block
+
+    def configure_optimizers(self):
+        # models/module.py:237-243: AdamW over all parameters
+        cfg = self.optimizer_cfg
+        return torch.optim.AdamW(self.parameters(), lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+
+
+def allreduce_gradients(module: torch.nn.Module, group=None) -> int:
+    """Data-parallel gradient averaging for one process per GPU WITHOUT the DDP wrapper: one flat NCCL all-reduce
+    (NVLink/NVSwitch) over every parameter that received a gradient; parameters without one (`head_dist.*` in "mean"
+    mode) are skipped on every rank, which is what `find_unused_parameters=True` does in the reference
+    (ex_maest.py:57).  Returns the number of gradient elements reduced."""
+    import torch.distributed as dist
+
+    ps = [p for p in module.parameters() if p.grad is not None]
+    if not ps:
+        return 0
+    flat = torch.cat([p.grad.reshape(-1) for p in ps])
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat /= dist.get_world_size(group)
+    off = 0
+    for p in ps:
+        n = p.numel()
+        p.grad.copy_(flat[off: off + n].view_as(p.grad))
+        off += n
+    return off

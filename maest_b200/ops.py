@@ -105,15 +105,117 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
     return out
 
 
-def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 0) -> torch.Tensor:
-    """qkv [B*N, 3*heads*64] 16-bit -> o [B*N, heads*64] 16-bit."""
+def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 0, save_lse: bool = False):
+    """qkv [B*N, 3*heads*64] 16-bit -> o [B*N, heads*64] 16-bit (and, for training, lse fp32 [B, heads, N])."""
     _need_cuda(qkv)
     assert qkv.is_contiguous() and qkv.shape == (B * N, 3 * heads * 64)
     out = torch.empty((B * N, heads * 64), device=qkv.device, dtype=qkv.dtype)
+    lse = torch.empty((B, heads, N), device=qkv.device, dtype=torch.float32) if save_lse else None
     with torch.cuda.device(qkv.device):
         lib = _lib_for(qkv)
-        _lib.check(lib.maest_attention_fwd(qkv.data_ptr(), out.data_ptr(), B, N, heads, _TORCH2DT[qkv.dtype], variant,
+        _lib.check(lib.maest_attention_fwd(qkv.data_ptr(), out.data_ptr(), _p(lse), B, N, heads, _TORCH2DT[qkv.dtype], variant,
                                            _stream()), "attention")
+    return (out, lse) if save_lse else out
+
+
+def attention_bwd(qkv: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor, lse: torch.Tensor, B: int, N: int, heads: int = 12,
+                  out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """Gradient of `attention` w.r.t. the packed qkv activation: returns dqkv [B*N, 3*heads*64] 16-bit."""
+    _need_cuda(qkv, o, d_o, lse)
+    assert qkv.is_contiguous() and o.is_contiguous() and d_o.is_contiguous() and lse.is_contiguous()
+    assert o.dtype == qkv.dtype == d_o.dtype
+    dev = qkv.device
+    dqkv = out if out is not None else torch.empty_like(qkv)
+    delta = torch.empty((B, heads, N), device=dev, dtype=torch.float32)
+    dq32 = torch.empty((B * N, heads * 64), device=dev, dtype=torch.float32)
+    with torch.cuda.device(dev):
+        lib = _lib_for(qkv)
+        _lib.check(lib.maest_attention_bwd(qkv.data_ptr(), o.data_ptr(), d_o.data_ptr(), lse.data_ptr(), delta.data_ptr(),
+                                           dq32.data_ptr(), dqkv.data_ptr(), B, N, heads, _TORCH2DT[qkv.dtype], _stream()),
+                   "attention_bwd")
+    return dqkv
+
+
+def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
+         bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
+         aux16: Optional[torch.Tensor] = None, k_splits: int = 1) -> torch.Tensor:
+    """out[M,N] = epilogue(sum_k A(m,k) B(n,k)); a_mn / b_mn: operand stored [K, M] / [K, N] (see include/maest_b200.h)."""
+    _need_cuda(a, b, bias, out, resid, aux16)
+    assert a.dtype == b.dtype and a.dtype in (torch.float16, torch.bfloat16) and a.stride(-1) == 1 and b.stride(-1) == 1
+    if out is None:
+        odt = a.dtype if epilogue in (_lib.EPI_STORE16, _lib.EPI_GELU16, _lib.EPI_GELUBWD16) else torch.float32
+        out = torch.empty((M, N), device=a.device, dtype=odt)
+    if epilogue == _lib.EPI_RESID32 and resid is None:
+        resid = out
+    with torch.cuda.device(a.device):
+        lib = _lib_for(a)
+        _lib.check(lib.maest_gemm(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), _p(bias), M, N, K,
+                                  _TORCH2DT[a.dtype], epilogue, out.data_ptr(), out.stride(-2), _p(resid), None, 0, 0, 0,
+                                  _p(aux16), int(k_splits), _stream()), "gemm")
+    return out
+
+
+def wgrad_splits(M: int, N: int, K: int, sms: int = 148) -> int:
+    tiles = ((M + 127) // 128) * ((N + 255) // 256)
+    kb = (K + 63) // 64
+    return max(1, min((2 * sms + tiles - 1) // tiles, max(1, kb // 4)))
+
+
+def mixup(x: torch.Tensor, perm: torch.Tensor, lam: torch.Tensor) -> torch.Tensor:
+    """x [B, ...] (fp16|fp32) -> fp32 blend x*lam + x[perm]*(1-lam) (models/module.py:77-86)."""
+    _need_cuda(x, perm, lam)
+    x = x.contiguous()
+    B = x.shape[0]
+    L = x.numel() // B
+    out = torch.empty(x.shape, device=x.device, dtype=torch.float32)
+    with torch.cuda.device(x.device):
+        lib = _lib_for(x)
+        _lib.check(lib.maest_mixup_fwd(x.data_ptr(), _TORCH2DT[x.dtype], perm.to(torch.int32).contiguous().data_ptr(),
+                                       lam.float().contiguous().data_ptr(), out.data_ptr(), B, L, _stream()), "mixup")
+    return out
+
+
+def bce_logits(logits: torch.Tensor, targets: torch.Tensor):
+    """(loss scalar, dlogits) of F.binary_cross_entropy_with_logits (mean)."""
+    _need_cuda(logits, targets)
+    z = logits.float().contiguous()
+    y = targets.float().contiguous()
+    loss = torch.empty((), device=z.device, dtype=torch.float32)
+    dz = torch.empty_like(z)
+    with torch.cuda.device(z.device):
+        lib = _lib_for(z)
+        _lib.check(lib.maest_bce_logits_fwd(z.data_ptr(), y.data_ptr(), z.numel(), loss.data_ptr(), dz.data_ptr(), _stream()), "bce")
+    return loss, dz
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, op_dtype, dx16: Optional[torch.Tensor] = None):
+    _need_cuda(dy, x, dx)
+    rows = x.numel() // 768
+    with torch.cuda.device(x.device):
+        lib = _lib_for(x)
+        _lib.check(lib.maest_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
+                                           dx.data_ptr(), _p(dx16), op_dtype_code(op_dtype), dgamma.data_ptr(), dbeta.data_ptr(),
+                                           rows, _stream()), "layernorm_bwd")
+
+
+def colsum(x: torch.Tensor, out: torch.Tensor):
+    _need_cuda(x, out)
+    M, N = x.shape
+    with torch.cuda.device(x.device):
+        lib = _lib_for(x)
+        _lib.check(lib.maest_colsum(x.data_ptr(), _TORCH2DT[x.dtype], x.stride(0), M, N, out.data_ptr(), _stream()), "colsum")
+
+
+def cast_rows16(src: torch.Tensor, rows: int, op_dtype, rows_per_group: int = 0, group_stride: int = 0, row_offset: int = 0,
+                out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    _need_cuda(src)
+    dt = op_dtype_code(op_dtype)
+    if out is None:
+        out = torch.empty((rows, 768), device=src.device, dtype=_DT2TORCH[dt])
+    with torch.cuda.device(src.device):
+        lib = _lib_for(src)
+        _lib.check(lib.maest_cast_rows16(src.data_ptr(), out.data_ptr(), out.stride(0), rows, rows_per_group, group_stride,
+                                         row_offset, dt, _stream()), "cast_rows16")
     return out
 
 
@@ -142,7 +244,7 @@ def keep_ft_tensor(keep_f: Optional[Sequence[int]], keep_t: Optional[Sequence[in
 
 
 def patch_tokens(mel: torch.Tensor, w_pe16: torch.Tensor, conv_bias, freq_pe, time_pe, cls_token, dist_token,
-                 new_pos_embed, keep_ft: Optional[torch.Tensor] = None, t_offset: int = 0) -> torch.Tensor:
+                 new_pos_embed, keep_ft: Optional[torch.Tensor] = None, t_offset: int = 0, return_patches: bool = False):
     """mel [B,96,T] (fp32|fp16) -> tokens fp32 [B, 2+P, 768].  Parameter tensors in the reference's shapes."""
     _need_cuda(mel, w_pe16)
     assert mel.dim() == 3 and mel.is_contiguous() and mel.dtype in (torch.float32, torch.float16)
@@ -161,6 +263,9 @@ def patch_tokens(mel: torch.Tensor, w_pe16: torch.Tensor, conv_bias, freq_pe, ti
             conv_bias.data_ptr(), freq_pe.data_ptr(), Fp, time_pe.data_ptr(), Wt, cls_token.data_ptr(),
             dist_token.data_ptr(), new_pos_embed.data_ptr(), _p(keep_ft), P, int(t_offset), tokens.data_ptr(),
             ws.data_ptr(), ws_bytes, _stream()), "patch_tokens")
+    if return_patches:   # the gathered patch operand [B*P, 256] (op16) is the B operand of the conv weight gradient
+        a16 = ws[: B * P * 512].view(w_pe16.dtype).view(B * P, 256)
+        return tokens, a16
     return tokens
 
 

@@ -1,0 +1,168 @@
+"""Training step of the MAEST hot path on the B200 kernels: forward with saved activations + hand-written backward,
+wrapped in ONE `torch.autograd.Function` so that Lightning / DDP / AdamW see ordinary parameters and `.grad`s.
+
+Forward (train mode): [mixup] -> patch tokens (+pos-embed, +patchout) -> 12 x (LN, qkv, attention, proj+residual, LN,
+fc1+GELU, fc2+residual) -> final LN of rows 0/1, (cls+dist)/2, head -> BCE-with-logits   (models/module.py:73-102).
+Backward mirrors it with the same tcgen05 GEMM kernel reading every operand in its natural layout
+(input gradients: B MN-major; weight gradients: both operands MN-major, split-K with fp32 atomics).
+torch is used for memory, autograd bookkeeping and (in DDP) the NCCL all-reduce only.
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import torch
+
+from . import _lib, ops
+
+E = 768
+
+
+def _flat_params(model):
+    return [(n, p) for n, p in model.named_parameters()]
+
+
+class MaestTrainStep(torch.autograd.Function):
+    """loss, logits = MaestTrainStep.apply(model, mel, targets, keep_ft, t_offset, *parameters)"""
+
+    @staticmethod
+    def forward(ctx, model, mel, targets, keep_ft, t_offset, *params):
+        dt = model.op_dtype
+        dev = mel.device
+        names = [n for n, _ in _flat_params(model)]
+        P_ = dict(zip(names, params))
+        f32 = lambda n: P_[n].detach().float().contiguous()            # noqa: E731
+        w16 = lambda n: model._weight16(n, P_[n + ".weight"])          # noqa: E731
+        if mel.dim() == 4:
+            mel = mel[:, 0]
+        if mel.dtype not in (torch.float32, torch.float16):
+            mel = mel.float()
+        tok, a16 = ops.patch_tokens(
+            mel.contiguous(), w16("patch_embed.proj"), f32("patch_embed.proj.bias"),
+            f32("freq_new_pos_embed").reshape(E, -1), f32("time_new_pos_embed").reshape(E, -1), f32("cls_token").reshape(-1),
+            f32("dist_token").reshape(-1), f32("new_pos_embed").reshape(2, E), keep_ft=keep_ft, t_offset=t_offset,
+            return_patches=True)
+        B, N, _ = tok.shape
+        M = B * N
+        x = tok.view(M, E)
+        saved = []
+        for i in range(len(model.blocks)):
+            pre = f"blocks.{i}."
+            h1, mean1, rstd1 = ops.layernorm16(x, f32(pre + "norm1.weight"), f32(pre + "norm1.bias"), 1e-6, dt, save_stats=True)
+            qkv = ops.linear(h1, w16(pre + "attn.qkv"), f32(pre + "attn.qkv.bias"), _lib.EPI_STORE16)
+            o, lse = ops.attention(qkv, B, N, 12, model.attn_variant, save_lse=True)
+            x_mid = torch.empty_like(x)
+            ops.linear(o, w16(pre + "attn.proj"), f32(pre + "attn.proj.bias"), _lib.EPI_RESID32, resid=x, out=x_mid)
+            h2, mean2, rstd2 = ops.layernorm16(x_mid, f32(pre + "norm2.weight"), f32(pre + "norm2.bias"), 1e-6, dt, save_stats=True)
+            upre = torch.empty((M, 4 * E), device=dev, dtype=h2.dtype)
+            u = ops.gemm(h2, w16(pre + "mlp.fc1"), _lib.EPI_GELU16, M, 4 * E, E, bias=f32(pre + "mlp.fc1.bias"), aux16=upre)
+            x_out = torch.empty_like(x)
+            ops.linear(u, w16(pre + "mlp.fc2"), f32(pre + "mlp.fc2.bias"), _lib.EPI_RESID32, resid=x_mid, out=x_out)
+            saved.append((x, mean1, rstd1, h1, qkv, lse, o, x_mid, mean2, rstd2, h2, upre, u))
+            x = x_out
+        logits, _, feats = ops.pool_head(x, B, N, f32("norm.weight"), f32("norm.bias"), f32("head.0.weight"), f32("head.0.bias"),
+                                         f32("head.1.weight"), f32("head.1.bias"))
+        loss, dlogits = ops.bce_logits(logits, targets)
+        ctx.model, ctx.names, ctx.saved, ctx.x_final = model, names, saved, x
+        ctx.dims = (B, N, int(a16.shape[0] // B), mel.shape[-1], int(t_offset))
+        ctx.keep_ft, ctx.a16, ctx.dlogits = keep_ft, a16, dlogits
+        ctx.params = P_
+        ctx.mark_non_differentiable(logits)
+        return loss, logits
+
+    @staticmethod
+    def backward(ctx, dloss, _dlogits_unused):
+        model, names, P_ = ctx.model, ctx.names, ctx.params
+        dt = model.op_dtype
+        B, N, P, T, t_off = ctx.dims
+        M = B * N
+        dev = dloss.device
+        f32 = lambda n: P_[n].detach().float().contiguous()            # noqa: E731
+        w16 = lambda n: model._weight16(n, P_[n + ".weight"])          # noqa: E731
+        G = {n: torch.zeros(P_[n].shape, device=dev, dtype=torch.float32) for n in names if not n.startswith("head_dist")}
+        g2 = lambda n, r, c: G[n].view(r, c)                           # noqa: E731
+        # fp16 operands need loss scaling (the reference's "16-mixed" uses GradScaler); bf16 does not.  The scale is applied
+        # to d(loss) on the way in and divided out of the fp32 parameter gradients on the way out.
+        ls = float(getattr(model, "train_loss_scale", None) or (4096.0 if ops.op_dtype_code(dt) == ops.F16 else 1.0))
+        gscale = (dloss.detach().float().reshape(1) * ls).contiguous()
+        lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+        st = torch.cuda.current_stream().cuda_stream
+        C_ = P_["head.1.weight"].shape[0]
+
+        dx = torch.zeros((M, E), device=dev, dtype=torch.float32)
+        hz = torch.empty((B, E), device=dev, dtype=torch.float32)
+        _lib.check(lib.maest_head_bwd(ctx.x_final.data_ptr(), B, N, ctx.dlogits.data_ptr(), gscale.data_ptr(),
+                                      f32("norm.weight").data_ptr(), f32("norm.bias").data_ptr(), f32("head.0.weight").data_ptr(),
+                                      f32("head.0.bias").data_ptr(), f32("head.1.weight").data_ptr(), C_, dx.data_ptr(), hz.data_ptr(),
+                                      G["norm.weight"].data_ptr(), G["norm.bias"].data_ptr(), G["head.0.weight"].data_ptr(),
+                                      G["head.0.bias"].data_ptr(), G["head.1.weight"].data_ptr(), G["head.1.bias"].data_ptr(), st),
+                   "head_bwd")
+        dx16 = ops.cast_rows16(dx, M, dt)
+        dh = torch.empty((M, E), device=dev, dtype=torch.float32)
+        dupre = torch.empty((M, 4 * E), device=dev, dtype=dx16.dtype)
+        d_o = torch.empty((M, E), device=dev, dtype=dx16.dtype)
+        dqkv = torch.empty((M, 3 * E), device=dev, dtype=dx16.dtype)
+
+        def wgrad(dy16, x16, n_out, n_in, gname):
+            ops.gemm(dy16, x16, _lib.EPI_ATOMIC32, n_out, n_in, M, a_mn=True, b_mn=True, out=g2(gname, n_out, n_in),
+                     k_splits=ops.wgrad_splits(n_out, n_in, M))
+
+        for i in reversed(range(len(model.blocks))):
+            pre = f"blocks.{i}."
+            x_in, mean1, rstd1, h1, qkv, lse, o, x_mid, mean2, rstd2, h2, upre, u = ctx.saved[i]
+            # ---- MLP branch: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
+            wgrad(dx16, u, E, 4 * E, pre + "mlp.fc2.weight")
+            ops.colsum(dx, G[pre + "mlp.fc2.bias"])
+            ops.gemm(dx16, w16(pre + "mlp.fc2"), _lib.EPI_GELUBWD16, M, 4 * E, E, b_mn=True, out=dupre, aux16=upre)
+            wgrad(dupre, h2, 4 * E, E, pre + "mlp.fc1.weight")
+            ops.colsum(dupre, G[pre + "mlp.fc1.bias"])
+            ops.gemm(dupre, w16(pre + "mlp.fc1"), _lib.EPI_STORE32, M, E, 4 * E, b_mn=True, out=dh)
+            ops.layernorm_bwd(dh, x_mid, mean2, rstd2, f32(pre + "norm2.weight"), dx, G[pre + "norm2.weight"], G[pre + "norm2.bias"],
+                              dt, dx16=dx16)
+            # ---- attention branch: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
+            wgrad(dx16, o, E, E, pre + "attn.proj.weight")
+            ops.colsum(dx, G[pre + "attn.proj.bias"])
+            ops.gemm(dx16, w16(pre + "attn.proj"), _lib.EPI_STORE16, M, E, E, b_mn=True, out=d_o)
+            ops.attention_bwd(qkv, o, d_o, lse, B, N, 12, out=dqkv)
+            wgrad(dqkv, h1, 3 * E, E, pre + "attn.qkv.weight")
+            ops.colsum(dqkv, G[pre + "attn.qkv.bias"])
+            ops.gemm(dqkv, w16(pre + "attn.qkv"), _lib.EPI_STORE32, M, E, 3 * E, b_mn=True, out=dh)
+            ops.layernorm_bwd(dh, x_in, mean1, rstd1, f32(pre + "norm1.weight"), dx, G[pre + "norm1.weight"], G[pre + "norm1.bias"],
+                              dt, dx16=dx16)
+            ctx.saved[i] = None
+        # ---- token assembly + patch embedding
+        Fp, Tp = 9, (T - 16) // 10 + 1
+        Wt = P_["time_new_pos_embed"].shape[-1]
+        dtok16 = ops.cast_rows16(dx, B * P, dt, rows_per_group=P, group_stride=2 + P, row_offset=2)
+        ops.gemm(dtok16, ctx.a16, _lib.EPI_ATOMIC32, E, 256, B * P, a_mn=True, b_mn=True, out=g2("patch_embed.proj.weight", E, 256),
+                 k_splits=ops.wgrad_splits(E, 256, B * P))
+        _lib.check(lib.maest_token_grad(dx.data_ptr(), B, N, P, Tp, Fp, Wt, t_off, ops._p(ctx.keep_ft), G["cls_token"].data_ptr(),
+                                        G["dist_token"].data_ptr(), G["new_pos_embed"].data_ptr(), G["patch_embed.proj.bias"].data_ptr(),
+                                        G["freq_new_pos_embed"].data_ptr(), G["time_new_pos_embed"].data_ptr(), st), "token_grad")
+        if ls != 1.0:
+            torch._foreach_mul_(list(G.values()), 1.0 / ls)
+        grads = tuple(G[n].to(P_[n].dtype) if n in G else None for n in names)   # head_dist.* get no gradient ("mean" mode)
+        return (None, None, None, None, None) + grads
+
+
+def training_forward(model, mel: torch.Tensor, targets: torch.Tensor, mix: Optional[tuple] = None):
+    """Train-mode forward + BCE loss with autograd support.  Host RNG draws follow the reference's order: the mixup draws
+    (if any) are made by the caller BEFORE this function (helpers/mixup.py:6-7), then time offset / patchout here."""
+    if model.distilled_type != "mean":
+        raise NotImplementedError("the fused training step implements distilled_type='mean' (every shipped training config)")
+    dev = model.cls_token.device
+    if dev.type != "cuda":
+        raise RuntimeError("maest_b200: training runs on CUDA (B200) only")
+    mel = mel.to(dev)
+    targets = targets.to(dev)
+    if mel.dim() == 4:
+        mel = mel[:, 0]
+    if mix is not None:
+        perm, lam = mix
+        mel = ops.mixup(mel, perm.to(dev), lam.to(dev))
+        targets = ops.mixup(targets, perm.to(dev), lam.to(dev))
+    Fp, Tp = (mel.shape[1] - 16) // 10 + 1, (mel.shape[2] - 16) // 10 + 1
+    t_offset, keep_f, keep_t, keep_seq = model._draw_patchout(Fp, Tp)
+    keep_ft = ops.keep_ft_tensor(keep_f, keep_t, Fp, Tp, keep_seq, dev)
+    params = [p for _, p in _flat_params(model)]
+    return MaestTrainStep.apply(model, mel, targets, keep_ft, t_offset, *params)

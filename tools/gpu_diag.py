@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
 
-CHECKS = ["logmel", "rowops", "gemm", "attn", "tokens", "e2e", "perf"]
+CHECKS = ["logmel", "rowops", "gemm", "attn", "tokens", "e2e", "perf", "bwdunits", "attnbwd", "train"]
 
 
 def rel(a, b):
@@ -292,6 +292,142 @@ def check_perf():
     wav = torch.rand(64, 480000, device=dev) * 2 - 1
     t = timeit(lambda: ops.logmel(wav))
     emit(check="perf", kernel="logmel", ms=t, gbs=(64 * 480000 * 4 + 64 * 96 * 1876 * 4) / t / 1e6)
+
+
+
+def check_bwdunits():
+    """Backward building blocks vs torch autograd / fp64 math."""
+    import torch
+    from maest_b200 import _lib, ops
+    g = torch.Generator().manual_seed(5)
+    for dt in (torch.float16, torch.bfloat16):
+        tol = 2e-3 if dt == torch.float16 else 1e-2
+        Mt, Nout, Kin = 1732, 768, 3072          # tokens, out features, in features (fc2-like)
+        dY = (torch.randn(Mt, Nout, generator=g) * 0.1).to(dt).cuda()
+        X = (torch.randn(Mt, Kin, generator=g) * 0.5).to(dt).cuda()
+        W = (torch.randn(Nout, Kin, generator=g) * 0.05).to(dt).cuda()
+        # input gradient: dX = dY @ W  (B MN-major)
+        dX = ops.gemm(dY, W, _lib.EPI_STORE32, Mt, Kin, Nout, b_mn=True)
+        emit(check="dgrad_store32", dt=str(dt), rel=rel(dX, dY.double() @ W.double()))
+        dX16 = ops.gemm(dY, W, _lib.EPI_STORE16, Mt, Kin, Nout, b_mn=True)
+        emit(check="dgrad_store16", dt=str(dt), rel=rel(dX16, dY.double() @ W.double()), ok=bool(rel(dX16, dY.double() @ W.double()) < tol))
+        # GELU backward epilogue
+        upre = (torch.randn(Mt, Kin, generator=g) * 1.5).to(dt).cuda()
+        up = upre.double().requires_grad_(True)
+        torch.nn.functional.gelu(up).backward(dY.double() @ W.double())
+        dU = ops.gemm(dY, W, _lib.EPI_GELUBWD16, Mt, Kin, Nout, b_mn=True, aux16=upre)
+        emit(check="dgrad_gelubwd16", dt=str(dt), rel=rel(dU, up.grad))
+        # weight gradient: dW = dY^T @ X  (both MN-major, split-K atomics)
+        for splits in (1, 3, ops.wgrad_splits(Nout, Kin, Mt)):
+            dW = torch.zeros(Nout, Kin, device="cuda")
+            ops.gemm(dY, X, _lib.EPI_ATOMIC32, Nout, Kin, Mt, a_mn=True, b_mn=True, out=dW, k_splits=splits)
+            r = rel(dW, dY.double().t() @ X.double())
+            emit(check="wgrad_atomic32", dt=str(dt), splits=splits, rel=r, ok=bool(r < 1e-5))
+            if r > 1e-3:
+                describe_mismatch(dW.cpu(), (dY.double().t() @ X.double()).float().cpu(), "wgrad", 1e-3)
+        # GELU16 with saved pre-activation
+        A = (torch.randn(300, 768, generator=g) * 0.5).to(dt).cuda()
+        W1 = (torch.randn(3072, 768, generator=g) * 0.05).to(dt).cuda()
+        b1 = torch.randn(3072, generator=g).cuda()
+        pre = torch.empty(300, 3072, device="cuda", dtype=dt)
+        u = ops.gemm(A, W1, _lib.EPI_GELU16, 300, 3072, 768, bias=b1, aux16=pre)
+        ref = A.double() @ W1.double().t() + b1.double()
+        emit(check="gelu16_aux", dt=str(dt), rel_pre=rel(pre, ref), rel_u=rel(u, torch.nn.functional.gelu(ref)))
+    # LayerNorm backward
+    rows = 1000
+    x = (torch.randn(rows, 768, generator=g) * 2 + 0.3)
+    gam = torch.randn(768, generator=g)
+    dy = torch.randn(rows, 768, generator=g)
+    dx0 = torch.randn(rows, 768, generator=g)
+    xd = x.double().requires_grad_(True)
+    gd = gam.double().requires_grad_(True)
+    bd = torch.zeros(768, dtype=torch.float64, requires_grad=True)
+    torch.nn.functional.layer_norm(xd, (768,), gd, bd, 1e-6).backward(dy.double())
+    _, mean, rstd = ops.layernorm16(x.cuda(), gam.cuda(), torch.zeros(768).cuda(), 1e-6, "fp16", save_stats=True)
+    dx = dx0.clone().cuda()
+    dg, db = torch.zeros(768).cuda(), torch.zeros(768).cuda()
+    dx16 = torch.empty(rows, 768, device="cuda", dtype=torch.float16)
+    ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dx, dg, db, "fp16", dx16=dx16)
+    emit(check="layernorm_bwd", rel_dx=rel(dx.cpu(), dx0.double() + xd.grad), rel_dgamma=rel(dg.cpu(), gd.grad), rel_dbeta=rel(db.cpu(), bd.grad),
+         rel_dx16=rel(dx16.cpu(), dx0.double() + xd.grad))
+    # colsum / cast_rows16 / mixup / bce
+    z = torch.randn(777, 2304, generator=g)
+    out = torch.zeros(2304).cuda()
+    ops.colsum(z.half().cuda(), out)
+    emit(check="colsum", rel=rel(out.cpu(), z.half().double().sum(0)))
+    src = torch.randn(3 * 52, 768, generator=g)
+    c = ops.cast_rows16(src.cuda(), 3 * 50, "bf16", rows_per_group=50, group_stride=52, row_offset=2)
+    emit(check="cast_rows16", ok=bool(torch.equal(c.cpu(), src.view(3, 52, 768)[:, 2:].reshape(150, 768).bfloat16())))
+    xm = torch.randn(4, 1, 96, 100, generator=g).half()
+    perm = torch.tensor([2, 0, 3, 1])
+    lam = torch.tensor([0.9, 0.6, 0.75, 0.51])
+    mx = ops.mixup(xm.cuda(), perm.cuda(), lam.cuda())
+    refm = xm.float() * lam.view(4, 1, 1, 1) + xm.float()[perm] * (1 - lam.view(4, 1, 1, 1))
+    emit(check="mixup", max_abs=float((mx.cpu() - refm).abs().max()))
+    lz = torch.randn(8, 400, generator=g) * 3
+    ly = (torch.rand(8, 400, generator=g) > 0.9).float()
+    loss, dz = ops.bce_logits(lz.cuda(), ly.cuda())
+    lzd = lz.double().requires_grad_(True)
+    lref = torch.nn.functional.binary_cross_entropy_with_logits(lzd, ly.double())
+    lref.backward()
+    emit(check="bce", loss_err=abs(float(loss) - float(lref)), rel_dz=rel(dz.cpu(), lzd.grad))
+
+
+def check_attnbwd():
+    import torch
+    from maest_b200 import ops
+    g = torch.Generator().manual_seed(6)
+    for dt in (torch.float16, torch.bfloat16):
+        for (B, N) in [(1, 128), (2, 100), (2, 866), (1, 300)]:
+            qkv = torch.randn(B * N, 2304, generator=g).to(dt).cuda()
+            d_o = (torch.randn(B * N, 768, generator=g) * 0.1).to(dt).cuda()
+            o, lse = ops.attention(qkv, B, N, 12, 0, save_lse=True)
+            qd = qkv.double().requires_grad_(True)
+            q, k, v = qd.view(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4)
+            s = (q @ k.transpose(-1, -2)) * 0.125
+            ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, 768)
+            ref.backward(d_o.double())
+            lse_ref = (torch.logsumexp(s, -1) * 1.4426950408889634)          # [B,12,N] in log2 units
+            dqkv = ops.attention_bwd(qkv, o, d_o, lse, B, N, 12)
+            torch.cuda.synchronize()
+            gq = qd.grad
+            emit(check="attn_bwd", dt=str(dt), B=B, N=N, lse_err=float((lse.double() - lse_ref).abs().max()),
+                 rel_dq=rel(dqkv[:, :768], gq[:, :768]), rel_dk=rel(dqkv[:, 768:1536], gq[:, 768:1536]),
+                 rel_dv=rel(dqkv[:, 1536:], gq[:, 1536:]), nan=int(torch.isnan(dqkv.float()).sum()))
+            if rel(dqkv, gq) > 0.05:
+                describe_mismatch(dqkv.float().cpu(), gq.float().cpu(), f"attn_bwd_{B}x{N}", 5e-2)
+
+
+def check_train():
+    """Full training step (mixup -> forward with patchout -> BCE -> backward) vs the reference's golden c4."""
+    import numpy as np
+    import torch
+    from maest_b200 import get_maest, synth
+    from maest_b200.train import training_forward
+    gold = dict(np.load(os.path.join(ROOT, "tests", "golden", "c4.npz")))
+    for dt in ("fp16", "bf16"):
+        m = get_maest(arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=400, input_f=96, input_t=1875, s_patchout_t=90, op_dtype=dt)
+        m.load_state_dict(synth.synth_state_dict(187, 400, seed=0), strict=False)
+        m = m.cuda().train()
+        x, y = synth.train_batch(2)
+        torch.manual_seed(1)
+        np.random.seed(1)
+        from maest_b200.module import my_mixup
+        mix = my_mixup(2, 0.3)
+        loss, logits = training_forward(m, x.cuda(), y.cuda(), mix)
+        loss.backward()
+        torch.cuda.synchronize()
+        res = dict(check="train", dt=dt, loss=float(loss), loss_ref=float(gold["loss"]), loss_err=abs(float(loss) - float(gold["loss"])))
+        grads = {n: p.grad for n, p in m.named_parameters()}
+        for k in ["cls_token", "time_new_pos_embed", "freq_new_pos_embed", "patch_embed.proj.bias", "blocks.0.norm1.weight",
+                  "blocks.0.attn.qkv.bias", "blocks.5.mlp.fc1.bias", "blocks.11.attn.proj.bias", "norm.weight", "head.0.bias", "head.1.bias"]:
+            res["g." + k] = round(rel(grads[k].cpu(), torch.tensor(gold["grad." + k])), 6)
+        for k in ["patch_embed.proj.weight", "blocks.0.attn.qkv.weight", "blocks.5.mlp.fc1.weight", "blocks.11.mlp.fc2.weight", "head.1.weight"]:
+            gk = grads[k]
+            res["gs." + k] = round(rel(gk.reshape(gk.shape[0], -1)[::37, ::29].cpu(), torch.tensor(gold["grad." + k + ".sub"])), 6)
+            res["gn." + k] = round(float(gk.double().norm()) / float(gold["gnorm." + k]), 6)
+        res["head_dist_none"] = grads["head_dist.weight"] is None
+        emit(**res)
 
 
 def main():

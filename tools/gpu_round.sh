@@ -2,11 +2,12 @@
 # One GPU-box session: diagnostics, parity tests, bench, ncu evidence.  Everything lands in gpurun_out/.
 set -u
 mkdir -p gpurun_out
-python tools/gpu_diag.py all gemm attn perf 2>&1 | tee gpurun_out/diag_stdout.txt | grep -v '"ok": true' | tail -60
+python tools/gpu_diag.py all ${DIAG:-attn perf bwdunits} 2>&1 | tee gpurun_out/diag_stdout.txt | grep -v '"ok": true' | tail -70
 echo "=== pytest -m gpu"
 python -m pytest tests -m gpu -q 2>&1 | tail -15 | tee gpurun_out/pytest_gpu.txt
 echo "=== bench"
 python bench.py --steps 10 --warmup 3 2>gpurun_out/bench_stderr.txt | tee gpurun_out/bench.json
+python bench.py --mode train --steps 5 --warmup 3 2>>gpurun_out/bench_stderr.txt | tee gpurun_out/bench_train.json
 tail -5 gpurun_out/bench_stderr.txt
 if [ "${NCU:-0}" = "1" ]; then
 echo "=== ncu launch list"
