@@ -67,6 +67,20 @@ int make_tmap(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t c
   return 0;
 }
 
+// fp32 [rows, cols] matrix, box = [box_rows, 32 floats] (128-byte inner extent), SWIZZLE_128B: target of the TMA reduce-add
+int make_tmap_f32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  if (!g_encode) return fail(-3, "maest_init() was not called");
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 4};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = g_encode(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(-5, "cuTensorMapEncodeTiled(f32) failed with %d", int(r));
+  return 0;
+}
+
 template <int DT, int EPI, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   const int splits = p.k_splits > 1 ? p.k_splits : 1;
@@ -84,7 +98,9 @@ int launch_gemm_dt(int epi, bool a_mn, bool b_mn, const CUtensorMap& ta, const C
   if (!a_mn && !b_mn) {
     switch (epi) {
       case MAEST_EPI_STORE16: return launch_gemm<DT, EPI_STORE16, false, false>(ta, tb, p, st);
-      case MAEST_EPI_GELU16: return launch_gemm<DT, EPI_GELU16, false, false>(ta, tb, p, st);
+      case MAEST_EPI_GELU16:
+        if (p.aux16 != nullptr) return launch_gemm<DT, EPI_GELU16_SAVE, false, false>(ta, tb, p, st);
+        return launch_gemm<DT, EPI_GELU16, false, false>(ta, tb, p, st);
       case MAEST_EPI_RESID32: return launch_gemm<DT, EPI_RESID32, false, false>(ta, tb, p, st);
       case MAEST_EPI_STORE32: return launch_gemm<DT, EPI_STORE32, false, false>(ta, tb, p, st);
     }
@@ -111,6 +127,7 @@ int init_dt() {
   int r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE16, false, false>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_GELU16, false, false>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_GELU16_SAVE, false, false>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_RESID32, false, false>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE32, false, false>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE16, false, true>, GEMM_SMEM_BYTES))) return r;
@@ -366,10 +383,11 @@ int32_t maest_attention_bwd(const void* qkv, const void* o, const void* d_o, con
   if (H != 12) return fail(-1, "attention_bwd: H must be 12");
   cudaStream_t st = (cudaStream_t)stream;
   const long M = long(B) * N;
-  CUtensorMap tq, td;
+  CUtensorMap tq, td, tdq;
   int r;
   if ((r = make_tmap(&tq, qkv, op_dtype, M, 3 * H * 64, 3 * H * 64, 128))) return r;
   if ((r = make_tmap(&td, d_o, op_dtype, M, H * 64, H * 64, 128))) return r;
+  if ((r = make_tmap_f32(&tdq, dq32, M, H * 64, H * 64, 128))) return r;
   CUDA_OK(cudaMemsetAsync(dq32, 0, size_t(M) * H * 64 * sizeof(float), st));
   AttnBwdParams p;
   p.B = B; p.N = N; p.H = H; p.lse = lse; p.delta = delta; p.dq32 = dq32; p.dqkv16 = dqkv;
@@ -379,11 +397,11 @@ int32_t maest_attention_bwd(const void* qkv, const void* o, const void* d_o, con
   const int cast_blocks = int((M + 7) / 8);
   if (op_dtype == MAEST_BF16) {
     attn_delta_kernel<DT_BF16><<<unsigned((nd + 255) / 256), 256, 0, st>>>(o, d_o, delta, B, N, H);
-    attention_bwd_kernel<DT_BF16><<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, st>>>(tq, td, p);
+    attention_bwd_kernel<DT_BF16><<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, st>>>(tq, td, tdq, p);
     cast_rows16_kernel<DT_BF16><<<cast_blocks, 256, 0, st>>>(dq32, dqkv, 3 * H * 64, int(M), 0x7fffffff, 0, 0);
   } else if (op_dtype == MAEST_F16) {
     attn_delta_kernel<DT_F16><<<unsigned((nd + 255) / 256), 256, 0, st>>>(o, d_o, delta, B, N, H);
-    attention_bwd_kernel<DT_F16><<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, st>>>(tq, td, p);
+    attention_bwd_kernel<DT_F16><<<grid, ATTB_THREADS, ATTB_SMEM_BYTES, st>>>(tq, td, tdq, p);
     cast_rows16_kernel<DT_F16><<<cast_blocks, 256, 0, st>>>(dq32, dqkv, 3 * H * 64, int(M), 0x7fffffff, 0, 0);
   } else return fail(-1, "attention_bwd: op_dtype must be f16/bf16");
   CUDA_OK(cudaGetLastError());
@@ -442,7 +460,10 @@ int32_t maest_layernorm_bwd(const float* dy, const float* x, const float* mean, 
 
 int32_t maest_colsum(const void* in, int32_t in_dtype, int64_t ld, int32_t M, int32_t N, float* out, void* stream) {
   if (M <= 0 || N <= 0) return 0;
-  dim3 grid((N + 255) / 256, M < 128 ? M : 128);
+  if (N % 8 || ld % 8) return fail(-1, "colsum: N and ld must be multiples of 8");
+  int splits = (M + 255) / 256;
+  splits = splits < 1 ? 1 : (splits > 64 ? 64 : splits);
+  dim3 grid((N + 255) / 256, splits);
   cudaStream_t st = (cudaStream_t)stream;
   if (in_dtype == MAEST_F32) colsum_kernel<float><<<grid, 256, 0, st>>>(reinterpret_cast<const float*>(in), ld, M, N, out);
   else if (in_dtype == MAEST_F16) colsum_kernel<__half><<<grid, 256, 0, st>>>(reinterpret_cast<const __half*>(in), ld, M, N, out);

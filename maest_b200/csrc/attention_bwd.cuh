@@ -8,14 +8,15 @@
 // written as 16-bit tiles to shared memory in the SWIZZLE_128B layout, where the same bytes serve as a K-major
 // A operand (dQ) and as an MN-major A operand (dV, dK).  Q, K, dO are consumed in their natural [row][d] layout
 // (K-major for S / dP, MN-major B for dK / dQ / dV) — no transposes are materialised anywhere.
-// dQ tiles are reduced across key tiles with fp32 atomics into dq32; dK/dV are written once as 16-bit.
+// dQ tiles are reduced across key tiles by the TMA engine (cp.reduce.async.bulk.tensor .add on fp32, staged through a
+// swizzled smem tile) into dq32; dK/dV are written once as 16-bit.
 #pragma once
 #include "attention.cuh"
 
 namespace mb {
 
 constexpr int ATTB_THREADS = 192;
-constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 10 + 128;   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves)
+constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 12 + 128;   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves), dQ staging (2 x [128 x 32] fp32)
 
 struct AttnBwdParams {
   int B, N, H;
@@ -29,7 +30,7 @@ struct AttnBwdParams {
 template <int DT>
 __global__ void __launch_bounds__(ATTB_THREADS, 1)
 attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_constant__ CUtensorMap tmap_do,
-                     const AttnBwdParams p) {
+                     const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using O16 = Op16<DT>;
   uint8_t* sK = smem;
@@ -38,6 +39,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   uint8_t* sdO = smem + 4 * ATT_TILE_BYTES;   // [2]
   uint8_t* sP = smem + 6 * ATT_TILE_BYTES;    // two [128 q x 64 keys] halves
   uint8_t* sdS = smem + 8 * ATT_TILE_BYTES;   // two halves
+  uint8_t* sdQ = smem + 10 * ATT_TILE_BYTES;  // two [128 rows x 32 fp32] SWIZZLE_128B halves (TMA reduce source)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATTB_SMEM_BYTES - 128);
   uint64_t* kv_full = bars;          // 1
   uint64_t* qdo_full = bars + 1;     // [2]
@@ -66,7 +68,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     fence_mbar_init();
   }
   if (warp == 4) {
-    if (lane == 0) { tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do); }
+    if (lane == 0) { tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_dq); }
     tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
@@ -146,18 +148,29 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     const uint32_t lane_off = uint32_t(warp * 32) << 16;
     const float sc = p.scale_log2, scale = p.scale;
     const long stat_base = (long(b) * p.H + h) * p.N;
-    auto drain_dq = [&](int i) {   // dQ_i: TMEM -> fp32 atomics
-      const int qrow = i * 128 + row;
-      float* dst = p.dq32 + long(row_base + qrow) * (p.H * 64) + h * 64;
+    auto compute_bar = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    // dQ_i: TMEM -> swizzled smem -> global fp32 reduce-add by the TMA engine.  Rows of the tile that lie beyond this
+    // clip carry dS = 0, hence dQ = 0, so adding them to the next clip's rows is harmless; rows beyond the tensor are clipped.
+    auto drain_dq = [&](int i) {
+      if (threadIdx.x == 0) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tile
+      compute_bar();
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
         tmem_ld32(tdQ + lane_off + uint32_t(c * 32), v);
         tc_wait_ld();
-        if (qrow < p.N) {
+        uint8_t* base = sdQ + c * ATT_TILE_BYTES + row * 128;
 #pragma unroll
-          for (int k = 0; k < 32; ++k) atomicAdd(dst + c * 32 + k, __uint_as_float(v[k]));
-        }
+        for (int q4 = 0; q4 < 8; ++q4)
+          *reinterpret_cast<uint4*>(base + ((q4 ^ (row & 7)) << 4)) = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+      }
+      fence_proxy_async_smem();
+      tc_fence_before();
+      compute_bar();
+      if (threadIdx.x == 0) {
+        tma_reduce_add_2d(&tmap_dq, sdQ, h * 64, row_base + i * 128);
+        tma_reduce_add_2d(&tmap_dq, sdQ + ATT_TILE_BYTES, h * 64 + 32, row_base + i * 128);
+        tma_store_commit();
       }
     };
     for (int i = 0; i < nq; ++i) {
@@ -207,6 +220,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     mbar_wait(mma2_done, (nq - 1) & 1);
     tc_fence_after();
     drain_dq(nq - 1);
+    if (threadIdx.x == 0) tma_store_wait<0>();
     // dK_j, dV_j -> 16-bit column blocks of dqkv
     const int key = kv0 + row;
     typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.dqkv16) + long(row_base + key) * (3 * p.H * 64) + h * 64;

@@ -33,6 +33,7 @@ enum : int {
   EPI_STORE32 = 3,  // out32[r,n] = acc + bias[n] + addend[(m % rows_per_group), n]
   EPI_GELUBWD16 = 4,  // out16[r,n] = acc * gelu'(aux16[r,n])                (fc2 dgrad fused with the GELU backward)
   EPI_ATOMIC32 = 5,   // out32[r,n] += acc  (red.global.add.f32; split-K weight gradients accumulate into .grad)
+  EPI_GELU16_SAVE = 6,  // EPI_GELU16 that also stores the pre-activation to aux16 (training forward)
 };
 
 struct GemmParams {
@@ -284,9 +285,9 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
           int pr = 0;
           if (identity_rows) { r = m; }
           else { pr = m % p.rows_per_group; r = long(m / p.rows_per_group) * p.group_stride + p.row_offset + pr; }
-          if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELUBWD16) {
-            if constexpr (EPI == EPI_GELU16) {
-              if (p.aux16 != nullptr) {   // training: keep the pre-activation for the backward pass
+          if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELUBWD16) {
+            if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE) {
+              if constexpr (EPI == EPI_GELU16_SAVE) {   // training: keep the pre-activation for the backward pass
                 uint2 pre;
                 pre.x = O::pack(a.x, a.y);
                 pre.y = O::pack(a.z, a.w);
