@@ -115,6 +115,8 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count() or 1)   # torchrun pins this to 1; the CPU arm uses every host core
+    os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
     import torch
     from maest_b200 import synth
     from oracle import maest_oracle as O
@@ -205,6 +207,8 @@ def run_train(args):
     op = "bf16" if args.op_dtype == "fp16" and not os.environ.get("MAEST_TRAIN_FP16") else args.op_dtype
     net = get_maest(arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=400, input_f=96, input_t=1875, s_patchout_t=90, op_dtype=op)
     net.load_state_dict(synth.synth_state_dict(187, 400, seed=0), strict=False)
+    if world > 1:
+        net.grad_allreduce = True          # per-block NCCL all-reduce of the flat gradient buffer, overlapped with backward
     mod = Module(net=net, mixup_alpha=0.3, do_swa=False).to(dev).train()
     opt = torch.optim.AdamW(mod.parameters(), lr=2e-5, weight_decay=1e-4, fused=True)
     torch.manual_seed(1 + rank)
@@ -220,7 +224,7 @@ def run_train(args):
         loss = mod.training_step(batch, 0)
         loss.backward()
         if world > 1:
-            n_grad[0] = allreduce_gradients(mod)
+            n_grad[0] = sum(p.numel() for p in mod.parameters() if p.grad is not None)
         opt.step()
         return loss
 
@@ -418,9 +422,15 @@ def main():
         gemm_flops = B * fl["linear"]
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         total_ms = sum(v["ms_per_step"] for v in breakdown.values())
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        if os.path.exists(tpath) and B == 64 and args.arch == "discogs-maest-30s-pw-129e":
+            with open(tpath) as tf:
+                traffic = json.load(tf)["gemm_family_bytes_per_step"] / gemm_launches    # measured DRAM bytes per launch (ncu --set full)
         line["roofline"] = dict(bound="tensor", kernel="gemm_tn_kernel (qkv/proj/fc1/fc2, 48 launches per step)", achieved=achieved,
                                 peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"],
-                                traffic=None, peak_source=peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
+                                traffic=traffic, algorithmic_flops_per_launch=gemm_flops / gemm_launches,
+                                algorithmic_bytes_per_launch=B * N * (2 * (768 + 2304) + 2 * 768 + 8 * 768 + 2 * (768 + 3072) + 2 * 3072 + 8 * 768) / 4, peak_source=peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                                 share_of_step=gemm_ms / total_ms, launches_per_step=gemm_launches)
         att = breakdown.get("attention")
         if att:

@@ -137,6 +137,7 @@ int init_dt() {
   if ((r = set_smem(attention_fwd_kernel<DT, true>, att_smem_bytes<true>()))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, false>, att_smem_bytes<false>()))) return r;
   if ((r = set_smem(attention_bwd_kernel<DT>, ATTB_SMEM_BYTES))) return r;
+  if ((r = set_smem(attention_fwd_split_kernel<DT>, ATT2_SMEM_BYTES))) return r;
   return 0;
 }
 
@@ -249,6 +250,13 @@ int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, i
   p.lse = lse;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, H, B);
   cudaStream_t st = (cudaStream_t)stream;
+  if (variant == 2) {
+    if (op_dtype == MAEST_BF16) attention_fwd_split_kernel<DT_BF16><<<grid, ATT2_THREADS, ATT2_SMEM_BYTES, st>>>(tq, p);
+    else if (op_dtype == MAEST_F16) attention_fwd_split_kernel<DT_F16><<<grid, ATT2_THREADS, ATT2_SMEM_BYTES, st>>>(tq, p);
+    else return fail(-1, "attention: op_dtype must be f16/bf16");
+    CUDA_OK(cudaGetLastError());
+    return 0;
+  }
   if (op_dtype == MAEST_BF16) {
     if (variant == 0) attention_fwd_kernel<DT_BF16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
     else attention_fwd_kernel<DT_BF16, false><<<grid, ATT_THREADS, att_smem_bytes<false>(), st>>>(tq, p);

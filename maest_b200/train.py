@@ -79,8 +79,29 @@ class MaestTrainStep(torch.autograd.Function):
         dev = dloss.device
         f32 = lambda n: P_[n].detach().float().contiguous()            # noqa: E731
         w16 = lambda n: model._weight16(n, P_[n + ".weight"])          # noqa: E731
-        G = {n: torch.zeros(P_[n].shape, device=dev, dtype=torch.float32) for n in names if not n.startswith("head_dist")}
+        # One flat fp32 gradient buffer in parameter order (embedding params | blocks 0..11 | norm + head); every
+        # parameter gradient is a view into it.  With `model.grad_allreduce` set (data-parallel run without the DDP
+        # wrapper) each block's slice is all-reduced over NCCL as soon as its backward has been enqueued, so the
+        # collective overlaps the remaining backward kernels; everything else about DDP stays outside.
+        gnames = [n for n in names if not n.startswith("head_dist")]
+        offs, total = {}, 0
+        for n in gnames:
+            offs[n] = total
+            total += P_[n].numel()
+        flat = torch.zeros(total, device=dev, dtype=torch.float32)
+        G = {n: flat[offs[n]: offs[n] + P_[n].numel()].view(P_[n].shape) for n in gnames}
         g2 = lambda n, r, c: G[n].view(r, c)                           # noqa: E731
+        sync = getattr(model, "grad_allreduce", None)
+        works = []
+
+        def reduce_range(first, last_exclusive):
+            if sync:
+                import torch.distributed as dist
+                grp = None if sync is True else sync
+                works.append(dist.all_reduce(flat[first:last_exclusive], op=dist.ReduceOp.SUM, group=grp, async_op=True))
+
+        blk_first = [offs[f"blocks.{i}.norm1.weight"] for i in range(len(model.blocks))]
+        blk_end = blk_first[1:] + [offs["norm.weight"]]
         # fp16 operands need loss scaling (the reference's "16-mixed" uses GradScaler); bf16 does not.  The scale is applied
         # to d(loss) on the way in and divided out of the fp32 parameter gradients on the way out.
         ls = float(getattr(model, "train_loss_scale", None) or (4096.0 if ops.op_dtype_code(dt) == ops.F16 else 1.0))
@@ -97,6 +118,7 @@ class MaestTrainStep(torch.autograd.Function):
                                       G["norm.weight"].data_ptr(), G["norm.bias"].data_ptr(), G["head.0.weight"].data_ptr(),
                                       G["head.0.bias"].data_ptr(), G["head.1.weight"].data_ptr(), G["head.1.bias"].data_ptr(), st),
                    "head_bwd")
+        reduce_range(offs["norm.weight"], total)                      # final norm + head gradients are complete
         dx16 = ops.cast_rows16(dx, M, dt)
         dh = torch.empty((M, E), device=dev, dtype=torch.float32)
         dupre = torch.empty((M, 4 * E), device=dev, dtype=dx16.dtype)
@@ -130,6 +152,7 @@ class MaestTrainStep(torch.autograd.Function):
             ops.layernorm_bwd(dh, x_in, mean1, rstd1, f32(pre + "norm1.weight"), dx, G[pre + "norm1.weight"], G[pre + "norm1.bias"],
                               dt, dx16=dx16)
             ctx.saved[i] = None
+            reduce_range(blk_first[i], blk_end[i])
         # ---- token assembly + patch embedding
         Fp, Tp = 9, (T - 16) // 10 + 1
         Wt = P_["time_new_pos_embed"].shape[-1]
@@ -139,8 +162,15 @@ class MaestTrainStep(torch.autograd.Function):
         _lib.check(lib.maest_token_grad(dx.data_ptr(), B, N, P, Tp, Fp, Wt, t_off, ops._p(ctx.keep_ft), G["cls_token"].data_ptr(),
                                         G["dist_token"].data_ptr(), G["new_pos_embed"].data_ptr(), G["patch_embed.proj.bias"].data_ptr(),
                                         G["freq_new_pos_embed"].data_ptr(), G["time_new_pos_embed"].data_ptr(), st), "token_grad")
-        if ls != 1.0:
-            torch._foreach_mul_(list(G.values()), 1.0 / ls)
+        reduce_range(0, blk_first[0])
+        scale = 1.0 / ls
+        if sync:
+            import torch.distributed as dist
+            for w in works:
+                w.wait()
+            scale /= dist.get_world_size(None if sync is True else sync)
+        if scale != 1.0:
+            flat.mul_(scale)
         grads = tuple(G[n].to(P_[n].dtype) if n in G else None for n in names)   # head_dist.* get no gradient ("mean" mode)
         return (None, None, None, None, None) + grads
 

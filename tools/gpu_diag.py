@@ -162,7 +162,7 @@ def check_attn():
             q, k, v = qkv.view(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4).double()
             s = (q @ k.transpose(-1, -2)) * 0.125
             ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, 768)
-            for variant in (0, 1):
+            for variant in (0, 1, 2):
                 try:
                     o = ops.attention(qkv, B, N, 12, variant)
                     torch.cuda.synchronize()
@@ -179,7 +179,7 @@ def check_attn():
     qkv = (torch.randn(B * N, 2304, generator=g) * 4).half().cuda()
     q, k, v = qkv.view(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4).double()
     ref = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125, -1) @ v).transpose(1, 2).reshape(B * N, 768)
-    for variant in (0, 1):
+    for variant in (0, 1, 2):
         o = ops.attention(qkv, B, N, 12, variant)
         emit(check="attn_sharp", variant=variant, rel=rel(o, ref))
 
@@ -219,7 +219,7 @@ def check_e2e():
     sd = synth.synth_state_dict(62, 400)
     x = synth.wave_a(2, 160000)
     for dt in ("fp16", "bf16"):
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             m = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, op_dtype=dt)
             m.attn_variant = variant
             m.load_state_dict(sd, strict=False)
@@ -285,7 +285,7 @@ def check_perf():
             emit(check="perf", kernel="cublas_" + nm, dt=str(dt), ms=tt, tflops=2.0 * M * Nn * K / tt / 1e9)
             del A, W, out
         qkv = torch.randn(M, 2304, device=dev).to(dt)
-        for variant in (0, 1):
+        for variant in (0, 1, 2):
             t = timeit(lambda: ops.attention(qkv, B, N, 12, variant))
             emit(check="perf", kernel="attention", dt=str(dt), variant=variant, ms=t, tflops=4.0 * B * 12 * N * N * 64 / t / 1e9)
         del qkv
