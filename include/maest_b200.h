@@ -103,6 +103,11 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
                    const float* resid, const float* addend, int32_t rows_per_group, int32_t group_stride,
                    int32_t row_offset, void* aux16, int32_t k_splits, void* stream);
 
+/* Tile shape of the forward (K-major) GEMMs: 0 = one CTA per 128x256 tile (cta_group::1), 1 = a CTA pair per 256x256 tile
+ * (cta_group::2, W tile shared by the two SMs of a TPC), 2 = per-shape choice (default).  Process-wide tuning switch;
+ * results are identical. */
+int32_t maest_set_gemm_mode(int32_t pair_mode);
+
 /* Fused multi-head attention, d_head 64.  Replaces Attention.forward lines models/maest.py:362-375.
  * qkv op16 [B*N, 3*H*64] as written by the qkv linear (columns = [q|k|v][head][64]); out op16 [B*N, H*64].
  * variant: 0 = P kept in TMEM (tcgen05.mma A-from-TMEM), 1 = P staged through shared memory.

@@ -40,6 +40,7 @@ SIGNATURES = {
                                    c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "maest_gemm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                              c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "maest_set_gemm_mode": (c_int32, [c_int32]),
     "maest_attention_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "maest_attention_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "maest_mixup_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),

@@ -9,6 +9,7 @@
 #include "attention.cuh"
 #include "attention_bwd.cuh"
 #include "gemm.cuh"
+#include "gemm2.cuh"
 #include "logmel.cuh"
 #include "logmel_tables.h"
 #include "rowops.cuh"
@@ -81,6 +82,26 @@ int make_tmap_f32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols,
   return 0;
 }
 
+int g_gemm_pair_mode = 2;   // 0: 1-CTA tiles, 1: CTA-pair (cta_group::2) tiles, 2: per-shape choice (default)
+
+// Measured on B200 (M = 107 840): the pair kernel wins where the mainloop dominates (qkv 0.322 -> 0.312 ms, fc2 0.434 -> 0.400 ms)
+// and loses where the epilogue does (proj 0.188 -> 0.197 ms, fc1+GELU 0.524 -> 0.543 ms).
+inline bool use_pair_kernel(int epi, int K) {
+  if (g_gemm_pair_mode != 2) return g_gemm_pair_mode == 1;
+  return epi == MAEST_EPI_STORE16 || (epi == MAEST_EPI_RESID32 && K >= 2048);
+}
+
+template <int DT, int EPI>
+int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  const int num_tiles = ((p.M + 255) / 256) * ((p.N + GEMM_BN - 1) / GEMM_BN);
+  const int sms = g_num_sms[cur_device()];
+  int pairs = sms / 2;
+  if (pairs > num_tiles) pairs = num_tiles;
+  gemm2_tn_kernel<DT, EPI><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, p);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 template <int DT, int EPI, bool A_MN, bool B_MN>
 int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
   const int splits = p.k_splits > 1 ? p.k_splits : 1;
@@ -95,6 +116,16 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
 // the instantiated (epilogue, operand-major) combinations: forward (K,K), dgrad (K,MN), wgrad (MN,MN)
 template <int DT>
 int launch_gemm_dt(int epi, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
+  if (!a_mn && !b_mn && p.k_splits <= 1 && use_pair_kernel(epi, p.K)) {
+    switch (epi) {
+      case MAEST_EPI_STORE16: return launch_gemm2<DT, EPI_STORE16>(ta, tb, p, st);
+      case MAEST_EPI_GELU16:
+        if (p.aux16 != nullptr) return launch_gemm2<DT, EPI_GELU16_SAVE>(ta, tb, p, st);
+        return launch_gemm2<DT, EPI_GELU16>(ta, tb, p, st);
+      case MAEST_EPI_RESID32: return launch_gemm2<DT, EPI_RESID32>(ta, tb, p, st);
+      case MAEST_EPI_STORE32: return launch_gemm2<DT, EPI_STORE32>(ta, tb, p, st);
+    }
+  }
   if (!a_mn && !b_mn) {
     switch (epi) {
       case MAEST_EPI_STORE16: return launch_gemm<DT, EPI_STORE16, false, false>(ta, tb, p, st);
@@ -134,6 +165,11 @@ int init_dt() {
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE32, false, true>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_GELUBWD16, false, true>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_ATOMIC32, true, true>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm2_tn_kernel<DT, EPI_STORE16>, GEMM2_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm2_tn_kernel<DT, EPI_GELU16>, GEMM2_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm2_tn_kernel<DT, EPI_GELU16_SAVE>, GEMM2_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm2_tn_kernel<DT, EPI_RESID32>, GEMM2_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm2_tn_kernel<DT, EPI_STORE32>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, true>, att_smem_bytes<true>()))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, false>, att_smem_bytes<false>()))) return r;
   if ((r = set_smem(attention_bwd_kernel<DT>, ATTB_SMEM_BYTES))) return r;
@@ -203,7 +239,8 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   int r;
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major operand: matrix [rows = K, cols = M|N]
   if ((r = a_mn ? make_tmap(&ta, a, op_dtype, K, M, lda, 64) : make_tmap(&ta, a, op_dtype, M, K, lda, GEMM_BM))) return r;
-  if ((r = b_mn ? make_tmap(&tb, b, op_dtype, K, N, ldb, 64) : make_tmap(&tb, b, op_dtype, N, K, ldb, GEMM_BN))) return r;
+  const bool pair_kernel = !a_mn && !b_mn && k_splits <= 1 && use_pair_kernel(epilogue, K);   // each CTA of a pair loads half of the W tile
+  if ((r = b_mn ? make_tmap(&tb, b, op_dtype, K, N, ldb, 64) : make_tmap(&tb, b, op_dtype, N, K, ldb, pair_kernel ? 128 : GEMM_BN))) return r;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = addend; p.ld_out = int(ld_out);
   p.aux16 = aux16; p.k_splits = k_splits;
@@ -235,6 +272,11 @@ int32_t maest_layernorm_fwd(const float* x, const float* w, const float* b, void
   else if (op_dtype == MAEST_F16) layernorm_to16_kernel<DT_F16><<<blocks, 256, 0, st>>>(x, w, b, y16, rows, eps, mean, rstd);
   else return fail(-1, "layernorm: op_dtype must be f16/bf16");
   CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_set_gemm_mode(int32_t pair_mode) {
+  g_gemm_pair_mode = pair_mode < 0 || pair_mode > 2 ? 2 : pair_mode;
   return 0;
 }
 

@@ -62,19 +62,20 @@ __device__ __forceinline__ float ex2_approx_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// 13 instructions (11 FMA-pipe + MUFU.RCP + MUFU.EX2): the argument is pre-scaled by sqrt(log2 e)/sqrt(2) so that
+// exp(-z^2) = ex2(-zs^2), and 0.5 x (1 + sign(x) erf|.|) is evaluated as fma(|0.5 x|, erf|.|, 0.5 x) (no copysign).
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));          // MUFU.RCP (1 ulp-ish; erf error budget is 1.5e-7)
+  const float zs = fabsf(x) * 0.84932180028801905f;                 // |x| / sqrt(2) * sqrt(log2 e)
+  const float t = rcp_approx(fmaf(0.2727374809f, zs, 1.0f));        // 0.3275911 / sqrt(log2 e)
   float p = fmaf(1.061405429f, t, -1.453152027f);
   p = fmaf(p, t, 1.421413741f);
   p = fmaf(p, t, -0.284496736f);
   p = fmaf(p, t, 0.254829592f);
   p *= t;
-  const float e = ex2_approx_ftz(-1.4426950408889634f * z * z);   // MUFU.EX2
+  const float e = ex2_approx_ftz(-zs * zs);
   const float erf_abs = fmaf(-p, e, 1.0f);
-  const float erf_v = copysignf(erf_abs, x);
   const float hx = 0.5f * x;
-  return fmaf(hx, erf_v, hx);
+  return fmaf(fabsf(hx), erf_abs, hx);
 }
 
 // d/dx [x Phi(x)] = Phi(x) + x phi(x), same erf approximation as the forward
@@ -89,6 +90,125 @@ __device__ __forceinline__ float gelu_erf_grad_fast(float x) {
   const float e = ex2_approx_ftz(-1.4426950408889634f * z * z);   // exp(-x^2 / 2)
   const float erf_v = copysignf(fmaf(-p, e, 1.0f), x);
   return fmaf(0.5f, erf_v, 0.5f) + x * e * 0.3989422804014327f;
+}
+
+// Drain one accumulator half-tile (32 TMEM lanes x up to 128 columns) of the calling epilogue warp: TMEM -> registers ->
+// swizzled per-warp smem tile -> row-coalesced fused epilogue.  m0 / n0: first output row / column of this warp's
+// sub-tile; `release_tmem()` is invoked once, as soon as the last accumulator column has been read.
+template <int DT, int EPI, typename ReleaseFn>
+__device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8_t* stg, uint32_t taddr, int m0, int n0, int lane,
+                                                      uint64_t* tfull, uint32_t aphase, ReleaseFn release_tmem) {
+  using O = Op16<DT == DT_BF16 ? DT_BF16 : DT_F16>;
+  const bool identity_rows = p.rows_per_group == 0x7fffffff;   // set by the host when no remap is requested
+  const int sub_row = lane >> 3;  // coalesced phase: 4 rows per instruction, 8 lanes x 16 B per row
+  const int c4 = lane & 7;
+  int nchunks = (p.N - n0 + 31) / 32;
+  nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
+  // RESID32: the residual tile does not depend on the accumulator, so its global loads are issued one chunk
+  // ahead (and, for chunk 0, before waiting for the accumulator) to keep HBM requests in flight.
+  float4 xr[8];
+  uint2 ar[8];   // GELUBWD16: the saved pre-activation tile, prefetched the same way
+  auto load_resid = [&](int cc) {
+    if constexpr (EPI == EPI_RESID32) {
+      const int col = n0 + cc * 32 + c4 * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + i * 4 + sub_row;
+        xr[i] = (m < p.M && cc < nchunks) ? *reinterpret_cast<const float4*>(p.resid + long(m) * p.ld_out + col)
+                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if constexpr (EPI == EPI_GELUBWD16) {
+      const int col = n0 + cc * 32 + c4 * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int m = m0 + i * 4 + sub_row;
+        ar[i] = (m < p.M && cc < nchunks) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const typename O::T*>(p.aux16) + long(m) * p.ld_out + col)
+                                          : make_uint2(0u, 0u);
+      }
+    }
+  };
+  load_resid(0);
+  mbar_wait(tfull, aphase);
+  tc_fence_after();
+  if (nchunks == 0) {
+    tc_fence_before();
+    release_tmem();
+  }
+#pragma unroll 1
+  for (int cc = 0; cc < nchunks; ++cc) {
+    const int n = n0 + cc * 32;
+    uint32_t v[32];
+    tmem_ld32(taddr + uint32_t(cc * 32), v);
+    tc_wait_ld();
+    if (cc == nchunks - 1) {   // accumulator fully drained by this warp: hand the TMEM stage back early
+      tc_fence_before();
+      release_tmem();
+    }
+    __syncwarp();              // previous chunk's staging reads are complete
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+          make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    }
+    __syncwarp();
+    const int col = n + c4 * 4;
+    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    float4 acc4[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = i * 4 + sub_row;
+      float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+      a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+      if constexpr (EPI == EPI_RESID32) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
+      acc4[i] = a;
+    }
+    if constexpr (EPI == EPI_RESID32) load_resid(cc + 1);   // next chunk's residual is in flight during the stores
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int rl = i * 4 + sub_row;
+      float4 a = acc4[i];
+      const int m = m0 + rl;
+      if (m >= p.M) continue;
+      long r;
+      int pr = 0;
+      if (identity_rows) { r = m; }
+      else { pr = m % p.rows_per_group; r = long(m / p.rows_per_group) * p.group_stride + p.row_offset + pr; }
+      if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELUBWD16) {
+        if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE) {
+          if constexpr (EPI == EPI_GELU16_SAVE) {   // training: keep the pre-activation for the backward pass
+            uint2 pre;
+            pre.x = O::pack(a.x, a.y);
+            pre.y = O::pack(a.z, a.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.aux16) + r * p.ld_out + col) = pre;
+          }
+          a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
+        }
+        if constexpr (EPI == EPI_GELUBWD16) {
+          const uint2 pre = *reinterpret_cast<const uint2*>(reinterpret_cast<const typename O::T*>(p.aux16) + r * p.ld_out + col);
+          const float2 u01 = O::unpack(pre.x), u23 = O::unpack(pre.y);
+          a.x *= gelu_erf_grad_fast(u01.x); a.y *= gelu_erf_grad_fast(u01.y);
+          a.z *= gelu_erf_grad_fast(u23.x); a.w *= gelu_erf_grad_fast(u23.y);
+        }
+        uint2 o;
+        o.x = O::pack(a.x, a.y);
+        o.y = O::pack(a.z, a.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.out) + r * p.ld_out + col) = o;
+      } else if constexpr (EPI == EPI_ATOMIC32) {
+        float* dst = reinterpret_cast<float*>(p.out) + r * p.ld_out + col;
+        atomicAdd(dst, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
+      } else if constexpr (EPI == EPI_RESID32) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
+      } else {
+        if (p.addend != nullptr) {
+          const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.addend + long(pr) * p.N + col));
+          a.x += d4.x; a.y += d4.y; a.z += d4.z; a.w += d4.w;
+        }
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
+      }
+    }
+  }
 }
 
 // A_MN / B_MN: the operand is stored with its M (resp. N) index contiguous and the reduction index as the row
@@ -207,118 +327,18 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       }
     }
   } else if (warp >= 4) {
-    using O = Op16<DT == DT_BF16 ? DT_BF16 : DT_F16>;
     const int e = warp - 4;
     const int q = warp & 3;        // TMEM lane quarter this warp may access
     const int half = e >> 2;       // which 128 accumulator columns this warp drains
     uint8_t* stg = stg_base + e * GEMM_STG_BYTES;
-    const bool identity_rows = p.rows_per_group == 0x7fffffff;   // set by the host when no remap is requested
-    const int sub_row = lane >> 3;  // coalesced phase: 4 rows per instruction, 8 lanes x 16 B per row
-    const int c4 = lane & 7;
     int as = 0;
     uint32_t aphase = 0;
     for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
       const int tile = t / splits;
       const int m0 = (tile / num_n) * GEMM_BM + q * 32;
       const int n0 = (tile % num_n) * GEMM_BN + half * 128;
-      int nchunks = (p.N - n0 + 31) / 32;
-      nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN + half * 128);
-      // RESID32: the residual tile does not depend on the accumulator, so its global loads are issued one chunk
-      // ahead (and, for chunk 0, before waiting for the accumulator) to keep HBM requests in flight.
-      float4 xr[8];
-      auto load_resid = [&](int cc) {
-        if constexpr (EPI == EPI_RESID32) {
-          const int col = n0 + cc * 32 + c4 * 4;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const int m = m0 + i * 4 + sub_row;
-            xr[i] = (m < p.M && cc < nchunks) ? *reinterpret_cast<const float4*>(p.resid + long(m) * p.ld_out + col)
-                                              : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-        }
-      };
-      load_resid(0);
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
-      if (nchunks == 0) {
-        tc_fence_before();
-        mbar_arrive(&tempty_bar[as]);
-      }
-#pragma unroll 1
-      for (int cc = 0; cc < nchunks; ++cc) {
-        const int n = n0 + cc * 32;
-        uint32_t v[32];
-        tmem_ld32(taddr + uint32_t(cc * 32), v);
-        tc_wait_ld();
-        if (cc == nchunks - 1) {   // accumulator fully drained by this warp: hand the TMEM stage back early
-          tc_fence_before();
-          mbar_arrive(&tempty_bar[as]);
-        }
-        __syncwarp();              // previous chunk's staging reads are complete
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-              make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-        __syncwarp();
-        const int col = n + c4 * 4;
-        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
-        float4 acc4[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + sub_row;
-          float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
-          a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-          if constexpr (EPI == EPI_RESID32) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
-          acc4[i] = a;
-        }
-        if constexpr (EPI == EPI_RESID32) load_resid(cc + 1);   // next chunk's residual is in flight during the stores
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int rl = i * 4 + sub_row;
-          float4 a = acc4[i];
-          const int m = m0 + rl;
-          if (m >= p.M) continue;
-          long r;
-          int pr = 0;
-          if (identity_rows) { r = m; }
-          else { pr = m % p.rows_per_group; r = long(m / p.rows_per_group) * p.group_stride + p.row_offset + pr; }
-          if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELUBWD16) {
-            if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE) {
-              if constexpr (EPI == EPI_GELU16_SAVE) {   // training: keep the pre-activation for the backward pass
-                uint2 pre;
-                pre.x = O::pack(a.x, a.y);
-                pre.y = O::pack(a.z, a.w);
-                *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.aux16) + r * p.ld_out + col) = pre;
-              }
-              a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
-            }
-            if constexpr (EPI == EPI_GELUBWD16) {
-              const uint2 pre = *reinterpret_cast<const uint2*>(reinterpret_cast<const typename O::T*>(p.aux16) + r * p.ld_out + col);
-              const float2 u01 = O::unpack(pre.x), u23 = O::unpack(pre.y);
-              a.x *= gelu_erf_grad_fast(u01.x); a.y *= gelu_erf_grad_fast(u01.y);
-              a.z *= gelu_erf_grad_fast(u23.x); a.w *= gelu_erf_grad_fast(u23.y);
-            }
-            uint2 o;
-            o.x = O::pack(a.x, a.y);
-            o.y = O::pack(a.z, a.w);
-            *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.out) + r * p.ld_out + col) = o;
-          } else if constexpr (EPI == EPI_ATOMIC32) {
-            float* dst = reinterpret_cast<float*>(p.out) + r * p.ld_out + col;
-            atomicAdd(dst, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
-          } else if constexpr (EPI == EPI_RESID32) {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
-          } else {
-            if (p.addend != nullptr) {
-              const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.addend + long(pr) * p.N + col));
-              a.x += d4.x; a.y += d4.y; a.z += d4.z; a.w += d4.w;
-            }
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
-          }
-        }
-      }
+      gemm_epilogue_subtile<DT, EPI>(p, stg, taddr, m0, n0, lane, &tfull_bar[as], aphase, [&]() { mbar_arrive(&tempty_bar[as]); });
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
   }

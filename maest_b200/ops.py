@@ -45,6 +45,13 @@ def _p(t: Optional[torch.Tensor]):
     return None if t is None else t.data_ptr()
 
 
+def set_gemm_mode(pair) -> None:
+    """Forward GEMM tile shape: False/0 = one CTA per 128x256 tile, True/1 = a CTA pair (cta_group::2) per 256x256 tile,
+    None/2 = per-shape choice (library default)."""
+    mode = 2 if pair is None else int(pair)
+    _lib.check(_lib.load().maest_set_gemm_mode(mode), "set_gemm_mode")
+
+
 def logmel(wav: torch.Tensor) -> torch.Tensor:
     """[B, S] (or [S]) fp32 CUDA waveform -> [B, 96, T] (or [96, T]) normalised log-mel."""
     _need_cuda(wav)

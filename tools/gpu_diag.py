@@ -17,7 +17,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 OUT = os.path.join(ROOT, "gpurun_out")
 
-CHECKS = ["logmel", "rowops", "gemm", "attn", "tokens", "e2e", "perf", "bwdunits", "attnbwd", "train"]
+CHECKS = ["logmel", "gemm2", "rowops", "gemm", "attn", "tokens", "e2e", "perf", "bwdunits", "attnbwd", "train"]
 
 
 def rel(a, b):
@@ -150,6 +150,36 @@ def check_gemm():
     ops.linear(A, W, None, _lib.EPI_STORE32, out=out.view(-1, N), addend=add, rows_per_group=P, group_stride=2 + P, row_offset=2)
     exp = (A.double() @ W.double().t()).view(6, P, N) + add.double()
     emit(check="gemm_remap", rel=rel(out[:, 2:], exp), rows01_untouched=bool((out[:, :2] == 0).all()))
+
+
+def check_gemm2():
+    """CTA-pair (cta_group::2) GEMM: correctness vs fp64 and speed vs the 1-CTA kernel."""
+    import torch
+    from maest_b200 import _lib, ops
+    ops.set_gemm_mode(True)
+    check_gemm()
+    M = 64 * 1685
+    for (Nn, K, epi, nm) in [(2304, 768, _lib.EPI_STORE16, "qkv"), (768, 768, _lib.EPI_RESID32, "proj"),
+                             (3072, 768, _lib.EPI_GELU16, "fc1"), (768, 3072, _lib.EPI_RESID32, "fc2")]:
+        A = (torch.randn(M, K, device="cuda") * 0.5).half()
+        W = (torch.randn(Nn, K, device="cuda") * 0.05).half()
+        bias = torch.randn(Nn, device="cuda")
+        out = torch.empty(M, Nn, device="cuda", dtype=torch.float16 if epi in (_lib.EPI_STORE16, _lib.EPI_GELU16) else torch.float32)
+        res = {}
+        for mode in (False, True):
+            ops.set_gemm_mode(mode)
+            fn = lambda: ops.linear(A, W, bias, epi, out=out, resid=out if epi == _lib.EPI_RESID32 else None)  # noqa: E731
+            fn()
+            torch.cuda.synchronize()
+            ts = []
+            for _ in range(6):
+                a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+                a.record(); fn(); b.record()
+                torch.cuda.synchronize()
+                ts.append(a.elapsed_time(b))
+            res["pair" if mode else "single"] = min(ts)
+        emit(check="gemm2_perf", kernel=nm, ms_single=res["single"], ms_pair=res["pair"], tflops_pair=2.0 * M * Nn * K / res["pair"] / 1e9)
+    ops.set_gemm_mode(None)
 
 
 def check_attn():
