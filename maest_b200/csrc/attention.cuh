@@ -15,6 +15,11 @@
 //   warp 5      MMA issuer: S = Q K^T (128x128x64), O += P V (128x64x128); V is consumed in its natural
 //               [key][d] layout as an MN-major B operand
 // P_IN_TMEM: P is stored back to TMEM (tcgen05.st) and fed as the A operand from TMEM (no smem round trip).
+//
+// Measured dead ends on B200 (config 3, per launch; baseline 0.889 ms): skipping the padded 32-key chunks of the last KV
+// tile 1.07 ms (per-chunk predicates defeat the scheduling of the hot loop); letting warps whose query rows are all
+// padding idle 0.889 ms (no change); polynomial exp2 for 25 % / 50 % of the scores 0.901 / 0.991 ms; two threads per
+// query row 1.33 ms.  The kernel is bound by the per-tile S read from TMEM plus the MUFU exponentials, not by issue slots.
 #pragma once
 #include "common.cuh"
 

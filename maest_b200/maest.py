@@ -379,8 +379,9 @@ class MAEST(nn.Module):
             self._f32(self.dist_token).reshape(-1), self._f32(self.new_pos_embed).reshape(2, EMBED),
             keep_ft=keep_ft, t_offset=t_offset)
 
-    def forward_features(self, x, transformer_block=-1, return_self_attention=False):
-        """x: [B,1,96,T] or [B,96,T] mel.  models/maest.py:634-829."""
+    def _encode(self, x, transformer_block=-1, return_self_attention=False):
+        """mel [B,1,96,T] | [B,96,T] -> residual stream after the requested blocks (transformer_block == -1: all blocks,
+        fp32 [B, N, 768], un-normalised) or the block-k embedding [B, 2304]."""
         if x.dim() == 4:
             x = x[:, 0]
         tok = self.tokens_from_mel(x)
@@ -390,7 +391,7 @@ class MAEST(nn.Module):
         depth = len(self.blocks)
         if transformer_block == -1:
             ops.encoder(xs, B, N, table, depth, False, self.op_dtype, self.attn_variant, self._workspace(B * N, xs.device))
-            return tok                      # un-normalised stream; pooling + final LN happen in pool_head
+            return tok                      # pooling + final LN happen in pool_head
         # the reference loops over all blocks and breaks at i == transformer_block (:812-820): an index that
         # never matches (negative other than -1, or >= depth) runs every block and ignores return_self_attention
         hit = 0 <= int(transformer_block) < depth
@@ -398,6 +399,23 @@ class MAEST(nn.Module):
         attn_only = bool(return_self_attention) and hit
         ops.encoder(xs, B, N, table, nb, attn_only, self.op_dtype, self.attn_variant, self._workspace(B * N, xs.device))
         return ops.block_embedding(tok, B, N)
+
+    def _head_params(self):
+        sep = self.distilled_type == "separated"
+        return (self._f32(self.norm.weight), self._f32(self.norm.bias), self._f32(self.head[0].weight), self._f32(self.head[0].bias),
+                self._f32(self.head[1].weight), self._f32(self.head[1].bias),
+                self._f32(self.head_dist.weight) if sep else None, self._f32(self.head_dist.bias) if sep else None)
+
+    def forward_features(self, x, transformer_block=-1, return_self_attention=False):
+        """Same return convention as the reference (models/maest.py:634-829): `(cls, dist)` after the final LayerNorm
+        for transformer_block == -1, else the [B, 2304] block embedding."""
+        out = self._encode(x, transformer_block, return_self_attention)
+        if transformer_block != -1:
+            return out
+        B, N, _ = out.shape
+        _, _, _, ln_cls, ln_dist = ops.pool_head(out, B, N, *self._head_params(), separated=self.distilled_type == "separated",
+                                                 save_ln=True)
+        return ln_cls, ln_dist
 
     def _workspace(self, rows: int, device):
         need = _lib.load().maest_encoder_workspace_bytes(rows)
@@ -454,16 +472,12 @@ class MAEST(nn.Module):
                 return None, torch.empty((0, 3 * EMBED), device=dev)
             return torch.empty((0, C_), device=dev), torch.empty((0, EMBED), device=dev)
 
-        out = self.forward_features(mel, transformer_block=transformer_block, return_self_attention=return_self_attention)
+        out = self._encode(mel, transformer_block=transformer_block, return_self_attention=return_self_attention)
         if transformer_block != -1:
             return None, out
         B, N, _ = out.shape
         sep = self.distilled_type == "separated"
-        logits, logits_dist, feats = ops.pool_head(
-            out, B, N, self._f32(self.norm.weight), self._f32(self.norm.bias), self._f32(self.head[0].weight),
-            self._f32(self.head[0].bias), self._f32(self.head[1].weight), self._f32(self.head[1].bias),
-            self._f32(self.head_dist.weight) if sep else None, self._f32(self.head_dist.bias) if sep else None,
-            separated=sep)
+        logits, logits_dist, feats = ops.pool_head(out, B, N, *self._head_params(), separated=sep)
         if sep:
             return logits, logits_dist, feats
         return logits, feats

@@ -216,6 +216,18 @@ def test_config2_logits_embeddings_vs_reference(m10, golden):
         assert rel(e, g["emb_block6_selfattn"]) < TOL_F16
 
 
+def test_forward_features_return_convention(m10):
+    # models/maest.py:804-810: forward_features(-1) returns the final-LayerNorm'ed (cls, dist) rows; forward's features = their mean
+    x = synth.wave_a(2, 160000).cuda()
+    with torch.no_grad():
+        mel = ops.logmel(x)
+        cls, dist = m10.forward_features(mel[:, None])
+        lo, feats = m10(x)
+        e6 = m10.forward_features(mel, transformer_block=6)
+    assert cls.shape == dist.shape == (2, 768) and e6.shape == (2, 2304)
+    assert rel((cls + dist) / 2, feats) < 1e-6
+
+
 def test_block_by_block_drift_vs_reference(m10, golden):
     g = golden["c2"]
     rows = list(g["row_probe"])
