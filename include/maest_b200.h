@@ -110,7 +110,9 @@ int32_t maest_set_gemm_mode(int32_t pair_mode);
 
 /* Fused multi-head attention, d_head 64.  Replaces Attention.forward lines models/maest.py:362-375.
  * qkv op16 [B*N, 3*H*64] as written by the qkv linear (columns = [q|k|v][head][64]); out op16 [B*N, H*64].
- * variant: 0 = P kept in TMEM (tcgen05.mma A-from-TMEM), 1 = P staged through shared memory.
+ * variant: 0 = default (P in TMEM, exponentials taken against the running max of the previous KV tiles with a verified
+ *   redo when a tile raises the max by more than 2^8, last KV tile narrowed to the real keys); 1 = max-first, P staged through
+ *   shared memory; 2 = max-first, P in TMEM.  All variants compute the same function (tests hold them to the same tolerance).
  * lse: optional fp32 [B, H, N] (may be NULL): per-row max + log2(sum) in the scaled log2 domain, saved for the backward pass. */
 int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t op_dtype,
                             int32_t variant, void* stream);

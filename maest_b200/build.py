@@ -32,6 +32,18 @@ def _stale() -> bool:
 SAFE_LIB_PATH = os.path.join(LIB_DIR, "libmaest_b200_safe.so")
 
 
+def build_variant(name: str, defines: list[str]) -> str:
+    """Experiment build: libmaest_b200_<name>.so with extra -D flags (A/B timing on the GPU box; select with MAEST_B200_LIB)."""
+    out = os.path.join(LIB_DIR, f"libmaest_b200_{name}.so")
+    os.makedirs(LIB_DIR, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if not f.startswith("--use_fast_math")] + [f"-D{d}" for d in defines]
+    cmd = [_nvcc(), *flags, "-o", out, *[os.path.join(CSRC, s) for s in SOURCES], "-lcudart"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    return out
+
+
 def build(force: bool = False, verbose: bool = False, safe: bool = False) -> str:
     """Compile csrc/*.cu for sm_100a into maest_b200/lib/libmaest_b200.so; returns the path.
     safe=True builds libmaest_b200_safe.so with -DMB_SAFE_WAIT (mbarrier waits trap after 2 s instead of hanging):

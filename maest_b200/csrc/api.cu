@@ -171,9 +171,9 @@ int init_dt() {
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_RESID32>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_STORE32>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, true>, att_smem_bytes<true>()))) return r;
+  if ((r = set_smem(attention_fwd_spec_kernel<DT, 128>, 120 * 1024))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, false>, att_smem_bytes<false>()))) return r;
   if ((r = set_smem(attention_bwd_kernel<DT>, ATTB_SMEM_BYTES))) return r;
-  if ((r = set_smem(attention_fwd_split_kernel<DT>, ATT2_SMEM_BYTES))) return r;
   return 0;
 }
 
@@ -292,20 +292,27 @@ int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, i
   p.lse = lse;
   dim3 grid((N + ATT_BQ - 1) / ATT_BQ, H, B);
   cudaStream_t st = (cudaStream_t)stream;
-  if (variant == 2) {
-    if (op_dtype == MAEST_BF16) attention_fwd_split_kernel<DT_BF16><<<grid, ATT2_THREADS, ATT2_SMEM_BYTES, st>>>(tq, p);
-    else if (op_dtype == MAEST_F16) attention_fwd_split_kernel<DT_F16><<<grid, ATT2_THREADS, ATT2_SMEM_BYTES, st>>>(tq, p);
-    else return fail(-1, "attention: op_dtype must be f16/bf16");
-    CUDA_OK(cudaGetLastError());
-    return 0;
+  if (op_dtype != MAEST_BF16 && op_dtype != MAEST_F16) return fail(-1, "attention: op_dtype must be f16/bf16");
+  const bool bf = op_dtype == MAEST_BF16;
+  switch (variant) {
+    case 0:    // default: speculative running max, peeled last KV tile
+      if (bf) attention_fwd_spec_kernel<DT_BF16, 128><<<grid, ATT_THREADS, AttSpecCfg<128>::kSmemLaunch, st>>>(tq, tq, p);
+      else attention_fwd_spec_kernel<DT_F16, 128><<<grid, ATT_THREADS, AttSpecCfg<128>::kSmemLaunch, st>>>(tq, tq, p);
+      break;
+    case 1:    // max-first kernel, P staged through shared memory
+      if (bf) attention_fwd_kernel<DT_BF16, false><<<grid, ATT_THREADS, att_smem_bytes<false>(), st>>>(tq, p);
+      else attention_fwd_kernel<DT_F16, false><<<grid, ATT_THREADS, att_smem_bytes<false>(), st>>>(tq, p);
+      break;
+    case 2:    // max-first kernel, P in TMEM (the round-1 baseline the default is measured against)
+      if (bf) attention_fwd_kernel<DT_BF16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
+      else attention_fwd_kernel<DT_F16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
+      break;
+    case 16:   // timing diagnostic: the default kernel forced to ONE CTA per SM by padding the dynamic smem request
+      if (bf) attention_fwd_spec_kernel<DT_BF16, 128><<<grid, ATT_THREADS, 120 * 1024, st>>>(tq, tq, p);
+      else attention_fwd_spec_kernel<DT_F16, 128><<<grid, ATT_THREADS, 120 * 1024, st>>>(tq, tq, p);
+      break;
+    default: return fail(-1, "attention: unknown variant %d", variant);
   }
-  if (op_dtype == MAEST_BF16) {
-    if (variant == 0) attention_fwd_kernel<DT_BF16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
-    else attention_fwd_kernel<DT_BF16, false><<<grid, ATT_THREADS, att_smem_bytes<false>(), st>>>(tq, p);
-  } else if (op_dtype == MAEST_F16) {
-    if (variant == 0) attention_fwd_kernel<DT_F16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
-    else attention_fwd_kernel<DT_F16, false><<<grid, ATT_THREADS, att_smem_bytes<false>(), st>>>(tq, p);
-  } else return fail(-1, "attention: op_dtype must be f16/bf16");
   CUDA_OK(cudaGetLastError());
   return 0;
 }
