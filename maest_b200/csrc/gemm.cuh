@@ -50,8 +50,7 @@ struct GemmParams {
   int rows_per_group, group_stride, row_offset;
 };
 
-// exact-erf GELU (models/maest.py:500 nn.GELU default).  erf via Abramowitz-Stegun 7.1.26
-// (|abs err| <= 1.5e-7, below fp32 epsilon of the 0.5*x*(1+erf) product for |x| < 1).
+// erf-form GELU (models/maest.py:500 nn.GELU default; NOT the tanh approximation).
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
   asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -62,20 +61,22 @@ __device__ __forceinline__ float ex2_approx_ftz(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-// 13 instructions (11 FMA-pipe + MUFU.RCP + MUFU.EX2): the argument is pre-scaled by sqrt(log2 e)/sqrt(2) so that
-// exp(-z^2) = ex2(-zs^2), and 0.5 x (1 + sign(x) erf|.|) is evaluated as fma(|0.5 x|, erf|.|, 0.5 x) (no copysign).
+// 12 instructions, ONE MUFU: erfc(|x|/sqrt 2) = 2^q(|x|) with q a degree-7 polynomial without constant term (weighted
+// least-squares fit of log2 erfc on |x| <= 4 sqrt 2, tools/fit_gelu_poly.py: |gelu error| <= 6e-7 absolute and <= 6e-5 relative
+// wherever |gelu| > 1e-4, i.e. well inside the 2.4e-4 rounding of the 16-bit output), then
+// 0.5 x (1 + sign(x) erf|.|) = fma(|0.5 x|, 1 - erfc, 0.5 x).  The epilogue of the fc1 GEMM is MUFU- and issue-limited
+// (two MUFU per element kept the XU pipe 67 % busy relative to the tile's MMA time), hence one exponential and no reciprocal.
 __device__ __forceinline__ float gelu_erf_fast(float x) {
-  const float zs = fabsf(x) * 0.84932180028801905f;                 // |x| / sqrt(2) * sqrt(log2 e)
-  const float t = rcp_approx(fmaf(0.2727374809f, zs, 1.0f));        // 0.3275911 / sqrt(log2 e)
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  const float e = ex2_approx_ftz(-zs * zs);
-  const float erf_abs = fmaf(-p, e, 1.0f);
+  const float ax = fminf(fabsf(x), 5.65685425f);
+  float q = fmaf(-5.775989393e-07f, ax, 3.963761264e-05f);
+  q = fmaf(q, ax, -7.848305395e-04f);
+  q = fmaf(q, ax, 8.050128818e-03f);
+  q = fmaf(q, ax, -5.326407775e-02f);
+  q = fmaf(q, ax, -4.589391351e-01f);
+  q = fmaf(q, ax, -1.151135445e+00f);
+  const float e = ex2_approx_ftz(q * ax);          // erfc(|x| / sqrt 2)
   const float hx = 0.5f * x;
-  return fmaf(fabsf(hx), erf_abs, hx);
+  return fmaf(fabsf(hx), 1.0f - e, hx);
 }
 
 // d/dx [x Phi(x)] = Phi(x) + x phi(x), same erf approximation as the forward
@@ -106,6 +107,27 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
   nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
   // RESID32: the residual tile does not depend on the accumulator, so its global loads are issued one chunk
   // ahead (and, for chunk 0, before waiting for the accumulator) to keep HBM requests in flight.
+  // EPI_STORE32 is the only epilogue with an output-row remap (patch tokens -> packed token buffer).  The remap needs an
+  // integer division per row, so it is done ONCE per sub-tile (doing it per 32-column chunk made the patch-embed GEMM epilogue
+  // 3x slower than its HBM bound); every other epilogue keeps the cheap r = m form and no extra live registers.
+  constexpr bool kRemap = (EPI == EPI_STORE32);
+  long orow_[kRemap ? 8 : 1];
+  int prow_[kRemap ? 8 : 1];
+  if constexpr (kRemap) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m0 + i * 4 + sub_row;
+      prow_[i] = 0;
+      if (m >= p.M) orow_[i] = -1;
+      else if (identity_rows) orow_[i] = m;
+      else { prow_[i] = m % p.rows_per_group; orow_[i] = long(m / p.rows_per_group) * p.group_stride + p.row_offset + prow_[i]; }
+    }
+  }
+  auto row_ok = [&](int i) -> bool { return m0 + i * 4 + sub_row < p.M; };
+  auto out_row = [&](int i) -> long {
+    if constexpr (kRemap) return orow_[i];
+    return long(m0 + i * 4 + sub_row);
+  };
   float4 xr[8];
   uint2 ar[8];   // GELUBWD16: the saved pre-activation tile, prefetched the same way
   auto load_resid = [&](int cc) {
@@ -113,18 +135,24 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
       const int col = n0 + cc * 32 + c4 * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int m = m0 + i * 4 + sub_row;
-        xr[i] = (m < p.M && cc < nchunks) ? *reinterpret_cast<const float4*>(p.resid + long(m) * p.ld_out + col)
-                                          : make_float4(0.f, 0.f, 0.f, 0.f);
+        xr[i] = (row_ok(i) && cc < nchunks) ? *reinterpret_cast<const float4*>(p.resid + out_row(i) * p.ld_out + col)
+                                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+    if constexpr (EPI == EPI_STORE32) {   // pos-embed table rows (L2-resident): same one-chunk-ahead prefetch
+      const int col = n0 + cc * 32 + c4 * 4;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        xr[i] = (p.addend != nullptr && row_ok(i) && cc < nchunks) ? __ldg(reinterpret_cast<const float4*>(p.addend + long(prow_[kRemap ? i : 0]) * p.N + col))
+                                                                      : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
     if constexpr (EPI == EPI_GELUBWD16) {
       const int col = n0 + cc * 32 + c4 * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int m = m0 + i * 4 + sub_row;
-        ar[i] = (m < p.M && cc < nchunks) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const typename O::T*>(p.aux16) + long(m) * p.ld_out + col)
-                                          : make_uint2(0u, 0u);
+        ar[i] = (row_ok(i) && cc < nchunks) ? *reinterpret_cast<const uint2*>(reinterpret_cast<const typename O::T*>(p.aux16) + out_row(i) * p.ld_out + col)
+                                               : make_uint2(0u, 0u);
       }
     }
   };
@@ -161,20 +189,15 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
       const int rl = i * 4 + sub_row;
       float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
       a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-      if constexpr (EPI == EPI_RESID32) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
+      if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
       acc4[i] = a;
     }
-    if constexpr (EPI == EPI_RESID32) load_resid(cc + 1);   // next chunk's residual is in flight during the stores
+    if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32) load_resid(cc + 1);   // next chunk's residual / table rows are in flight during the stores
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const int rl = i * 4 + sub_row;
       float4 a = acc4[i];
-      const int m = m0 + rl;
-      if (m >= p.M) continue;
-      long r;
-      int pr = 0;
-      if (identity_rows) { r = m; }
-      else { pr = m % p.rows_per_group; r = long(m / p.rows_per_group) * p.group_stride + p.row_offset + pr; }
+      if (!row_ok(i)) continue;
+      const long r = out_row(i);
       if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELUBWD16) {
         if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE) {
           if constexpr (EPI == EPI_GELU16_SAVE) {   // training: keep the pre-activation for the backward pass
@@ -201,10 +224,6 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
       } else if constexpr (EPI == EPI_RESID32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
       } else {
-        if (p.addend != nullptr) {
-          const float4 d4 = __ldg(reinterpret_cast<const float4*>(p.addend + long(pr) * p.N + col));
-          a.x += d4.x; a.y += d4.y; a.z += d4.z; a.w += d4.w;
-        }
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
       }
     }

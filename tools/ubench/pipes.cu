@@ -29,6 +29,11 @@ __global__ void bench(float* out, long long* cycles, float seed) {
       if (KIND == 6) { __half2 h = __floats2half2_rn(a[i], a[(i + 1) % UNROLL]); acc ^= *reinterpret_cast<unsigned*>(&h); }            // F2FP (+LOP)
       if (KIND == 7) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); a[(i + 8) % UNROLL] = fmaf(a[(i + 8) % UNROLL], b, c); a[(i + 4) % UNROLL] = a[(i + 4) % UNROLL] + c; }  // MUFU + FFMA + FADD
       if (KIND == 8) { a[i] = fmaf(a[i], b, c); a[(i + 8) % UNROLL] = fmaxf(a[(i + 8) % UNROLL], c); }   // FFMA + FMNMX (fma + alu pipes)
+      if (KIND == 10) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); __half2 h = __floats2half2_rn(a[(i + 8) % UNROLL], a[(i + 9) % UNROLL]); acc += *reinterpret_cast<unsigned*>(&h); }   // MUFU + F2FP + IADD
+      if (KIND == 11) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); float m; asm volatile("max.f32 %0, %1, %2, %3;" : "=f"(m) : "f"(a[(i + 8) % UNROLL]), "f"(a[(i + 9) % UNROLL]), "f"(b)); b = m; }   // MUFU + FMNMX3
+      if (KIND == 12) { __half2 h = __floats2half2_rn(a[i], a[(i + 1) % UNROLL]); acc += *reinterpret_cast<unsigned*>(&h); a[i] = a[i] + c; }   // F2FP + IADD + FADD
+      if (KIND == 13) { asm volatile("ex2.approx.ftz.f32 %0, %0;" : "+f"(a[i])); a[(i + 8) % UNROLL] = fmaf(a[(i + 8) % UNROLL], b, c); a[(i + 4) % UNROLL] = a[(i + 4) % UNROLL] + c;
+                        if (i & 1) { __half2 h = __floats2half2_rn(a[(i + 2) % UNROLL], a[(i + 3) % UNROLL]); acc += *reinterpret_cast<unsigned*>(&h); } }   // the softmax inner loop mix: MUFU + FFMA + FADD + 0.5 (F2FP + IADD)
       if (KIND == 9) { asm volatile("rcp.approx.ftz.f32 %0, %0;" : "+f"(a[i])); }   // MUFU.RCP
     }
   }
@@ -72,5 +77,9 @@ int main() {
   run<6>("F2FP.PACK + LOP", 2);
   run<7>("MUFU.EX2 + FFMA + FADD", 3);
   run<8>("FFMA + FMNMX", 2);
+  run<10>("MUFU.EX2 + F2FP + IADD", 3);
+  run<11>("MUFU.EX2 + FMNMX3", 2);
+  run<12>("F2FP + IADD + FADD", 3);
+  run<13>("softmax mix (4 instr)", 4);
   return 0;
 }
