@@ -8,7 +8,6 @@
 #include "../../include/maest_b200.h"
 #include "attention.cuh"
 #include "attention_bwd.cuh"
-#include "attention_pp.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "logmel.cuh"
@@ -173,7 +172,6 @@ int init_dt() {
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_STORE32>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, true>, att_smem_bytes<true>()))) return r;
   if ((r = set_smem(attention_fwd_spec_kernel<DT, 128>, 120 * 1024))) return r;
-  if ((r = set_smem(attention_fwd_pp_kernel<DT>, ATTP_SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, false>, att_smem_bytes<false>()))) return r;
   if ((r = set_smem(attention_bwd_kernel<DT>, ATTB_SMEM_BYTES))) return r;
   return 0;
@@ -301,15 +299,6 @@ int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, i
       if (bf) attention_fwd_spec_kernel<DT_BF16, 128><<<grid, ATT_THREADS, AttSpecCfg<128>::kSmemLaunch, st>>>(tq, tq, p);
       else attention_fwd_spec_kernel<DT_F16, 128><<<grid, ATT_THREADS, AttSpecCfg<128>::kSmemLaunch, st>>>(tq, tq, p);
       break;
-    case 3: {  // ping-pong: one persistent CTA per SM, two query tiles, softmax warpgroups alternate on the MUFU pipe
-      const int npairs = (N + 2 * ATT_BQ - 1) / (2 * ATT_BQ);
-      const long total = long(B) * H * npairs;
-      const int sms = g_num_sms[cur_device()];
-      const int ctas = int(total < sms ? total : sms);
-      if (bf) attention_fwd_pp_kernel<DT_BF16><<<ctas, ATTP_THREADS, ATTP_SMEM_BYTES, st>>>(tq, p);
-      else attention_fwd_pp_kernel<DT_F16><<<ctas, ATTP_THREADS, ATTP_SMEM_BYTES, st>>>(tq, p);
-      break;
-    }
     case 1:    // max-first kernel, P staged through shared memory
       if (bf) attention_fwd_kernel<DT_BF16, false><<<grid, ATT_THREADS, att_smem_bytes<false>(), st>>>(tq, p);
       else attention_fwd_kernel<DT_F16, false><<<grid, ATT_THREADS, att_smem_bytes<false>(), st>>>(tq, p);

@@ -130,7 +130,7 @@ def test_gelu_epilogue_matches_exact_erf_gelu():
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("BN", [(1, 128), (2, 100), (2, 560), (1, 1685), (3, 866), (1, 3)])
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2])
 def test_attention_vs_fp64(dt, BN, variant):
     B, N = BN
     g = torch.Generator().manual_seed(B * 1000 + N)
@@ -150,7 +150,7 @@ def test_attention_sharp_scores_and_rescale_path():
     qkv.view(N, 3, 12, 64)[400:, 1] *= 3
     q, k, v = qkv.view(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4).double()
     ref = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125, -1) @ v).transpose(1, 2).reshape(B * N, 768)
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2):
         assert rel(ops.attention(qkv, B, N, 12, variant), ref) < 1e-3
 
 
