@@ -59,6 +59,24 @@ int32_t maest_init(int32_t device);
  * wav fp32 [B, S] with row stride wav_stride (elements); mel fp32 [B, 96, T], T = 1 + S/256.  Requires S > 256. */
 int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, float* mel, void* stream);
 
+/* K1, dataset-file flavour.  Same STFT + mel + log compression, but the output is what the
+ * reference's offline extractor stores: UN-normalised log10(1 + 1e4 mel) as float16, time-major [B, T, 96]
+ * (helpers/melspectrogram_extractor.py:15-48 writes [frames, 96] float16 .mmap files; the z-norm is applied later by the
+ * data module).  Note: the reference extractor runs Essentia's framing, ours is the torchaudio framing of K1 (centre = True). */
+int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, void* stream);
+
+/* Loader -> device ingest.  Replaces, per batch, DiscogsDataset.load_melspectrogram's
+ * zero-pad + centring np.roll + transpose (discogs/dataset.py:120-139), DiscogsDataModule's norm_func
+ * ((x - mean) / (2 std) in float16 arithmetic, discogs/datamodule.py:126-137) and roll_func (torch.roll along time, :111-123).
+ *   raw_tm16    fp16 [B, T, 96]: the window bytes of each clip exactly as read from its .mmap file (time-major); rows
+ *               >= frames_read[b] are never read
+ *   frames_read int32 [B] (device) frames read from the file, <= T; NULL = T everywhere
+ *   roll_shift  int32 [B] (device) time shift per clip, NULL = none
+ *   out         fp16 [B, 1, 96, T]
+ * Bit-exact with the reference (same float16 rounding points). */
+int32_t maest_mel_ingest_fwd(const void* raw_tm16, const int32_t* frames_read, const int32_t* roll_shift, int32_t B, int32_t T,
+                             int32_t do_norm, float norm_mean, float norm_std, void* out, void* stream);
+
 /* K2 — mel -> packed token buffer.  Replaces PatchEmbed.forward (models/maest.py:243-256) and the pre-block part
  * of MAEST.forward_features (:645-800): + time/freq pos-embed, structured/unstructured patchout, flatten,
  * CLS/DIST rows.

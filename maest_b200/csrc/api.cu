@@ -8,6 +8,7 @@
 #include "../../include/maest_b200.h"
 #include "attention.cuh"
 #include "attention_bwd.cuh"
+#include "ingest.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "logmel.cuh"
@@ -182,7 +183,7 @@ int init_dt() {
 extern "C" {
 
 const char* maest_last_error(void) { return g_err; }
-int32_t maest_abi_version(void) { return 2; }
+int32_t maest_abi_version(void) { return 3; }
 
 int32_t maest_init(int32_t device) {
   if (device < 0 || device >= 64) return fail(-1, "bad device %d", device);
@@ -211,16 +212,44 @@ int32_t maest_init(int32_t device) {
   return 0;
 }
 
-int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, float* mel, void* stream) {
+static int32_t logmel_launch(const float* wav, int32_t B, int32_t S, int64_t wav_stride, float* mel, void* raw_tm16, void* stream) {
   const int dev = cur_device();
   if (!g_inited[dev]) return fail(-3, "maest_init() was not called for device %d", dev);
   if (B <= 0) return 0;
   if (S <= LM_HOP) return fail(-1, "waveform of %d samples is too short for reflect padding (need > 256)", S);
   LogMelParams p;
   p.wav = wav; p.wav_stride = wav_stride; p.B = B; p.S = S; p.T = 1 + S / LM_HOP; p.mel = mel;
+  p.raw_tm16 = reinterpret_cast<__half*>(raw_tm16);
   p.tables = g_lm_tables[dev];
   dim3 grid((p.T + LM_FRAMES - 1) / LM_FRAMES, B);
   logmel_kernel<<<grid, LM_THREADS, LM_SMEM_BYTES, (cudaStream_t)stream>>>(p);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, float* mel, void* stream) {
+  if (!mel) return fail(-1, "logmel: mel is NULL");
+  return logmel_launch(wav, B, S, wav_stride, mel, nullptr, stream);
+}
+
+int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, void* stream) {
+  if (!raw_tm16) return fail(-1, "logmel_raw16: output is NULL");
+  return logmel_launch(wav, B, S, wav_stride, nullptr, raw_tm16, stream);
+}
+
+int32_t maest_mel_ingest_fwd(const void* raw_tm16, const int32_t* frames_read, const int32_t* roll_shift, int32_t B, int32_t T,
+                             int32_t do_norm, float norm_mean, float norm_std, void* out, void* stream) {
+  if (B <= 0 || T <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(raw_tm16) & 3) != 0) return fail(-4, "mel_ingest: raw windows must be 4-byte aligned");
+  IngestParams p;
+  p.raw = reinterpret_cast<const __half*>(raw_tm16); p.frames_read = frames_read; p.roll_shift = roll_shift; p.B = B; p.T = T;
+  p.do_norm = do_norm;
+  // the reference's arithmetic: float16 array (op) Python float -> numpy rounds the scalar to float16 first
+  p.norm_mean = __float2half_rn(norm_mean);
+  p.norm_2std = __float2half_rn(norm_std * 2.0f);
+  p.out = reinterpret_cast<__half*>(out);
+  dim3 grid((T + ING_FRAMES - 1) / ING_FRAMES, B);
+  mel_ingest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -160,15 +160,16 @@ MB_HD void lm_power(int tid, const float* z_re, const float* z_im, float* powA, 
   }
 }
 
-// sparse triangular filterbank + log compression + z-norm for one (band, frame)
-MB_HD float lm_band(int band, const float* pw, const LogMelTables& tb) {
+// sparse triangular filterbank + log compression for one (band, frame): log10(1 + 1e4 x) = log2(.) * log10(2)
+MB_HD float lm_band_raw(int band, const float* pw, const LogMelTables& tb) {
   const int s = tb.band_start[band], n = tb.band_len[band];
   float acc = 0.f;
   for (int i = 0; i < n; ++i) acc = fmaf(pw[s + i], tb.band_w[band * LM_MAX_TAPS + i], acc);
-  // log10(1 + 1e4 x) = log2(.) * log10(2);   (x - 2.06755686098554) / (2 * 1.268292820667291)
-  const float lg = log2f(fmaf(acc, 10000.0f, 1.0f)) * 0.30102999566398120f;
-  return (lg - 2.06755686098554f) * 0.39423072641610746f;
+  return log2f(fmaf(acc, 10000.0f, 1.0f)) * 0.30102999566398120f;
 }
+// z-norm of the model input: (x - 2.06755686098554) / (2 * 1.268292820667291)   (models/helpers/melspectrogram.py:57-60)
+MB_HD float lm_znorm(float lg) { return (lg - 2.06755686098554f) * 0.39423072641610746f; }
+MB_HD float lm_band(int band, const float* pw, const LogMelTables& tb) { return lm_znorm(lm_band_raw(band, pw, tb)); }
 
 MB_HD int lm_reflect(int s, int S) {
   if (s < 0) s = -s;
@@ -181,7 +182,9 @@ struct LogMelParams {
   const float* wav;   // [B, wav_stride]
   long wav_stride;
   int B, S, T;
-  float* mel;         // [B, 96, T]
+  float* mel;         // [B, 96, T] normalised fp32 (model input), or null
+  __half* raw_tm16;   // [B, T, 96] un-normalised log10(1 + 1e4 mel) as fp16, time-major: the layout of the reference's
+                      // .mmap training files (helpers/melspectrogram_extractor.py:45-47), or null
   const LogMelTables* tables;
 };
 
@@ -238,16 +241,24 @@ __global__ void __launch_bounds__(LM_THREADS, 2) logmel_kernel(const LogMelParam
     gsync();
     for (int o = gt; o < 2 * LM_NMEL; o += 64) {
       const int which = o / LM_NMEL, band = o - which * LM_NMEL;
-      if (which == 0 || haveB) outs[band * LM_OUT_STRIDE + fa + which] = lm_band(band, bufB_re + which * 256, tb);
+      if (which == 0 || haveB) outs[band * LM_OUT_STRIDE + fa + which] = lm_band_raw(band, bufB_re + which * 256, tb);
     }
     gsync();
   }
   __syncthreads();
-  // coalesced store: consecutive threads -> consecutive frames of one band
-  float* mel = p.mel + long(b) * LM_NMEL * p.T;
-  for (int i = tid; i < LM_NMEL * LM_FRAMES; i += LM_THREADS) {
-    const int band = i / LM_FRAMES, f = i - band * LM_FRAMES;
-    if (f < nfr) mel[long(band) * p.T + t0 + f] = outs[band * LM_OUT_STRIDE + f];
+  if (p.mel != nullptr) {   // coalesced store: consecutive threads -> consecutive frames of one band
+    float* mel = p.mel + long(b) * LM_NMEL * p.T;
+    for (int i = tid; i < LM_NMEL * LM_FRAMES; i += LM_THREADS) {
+      const int band = i / LM_FRAMES, f = i - band * LM_FRAMES;
+      if (f < nfr) mel[long(band) * p.T + t0 + f] = lm_znorm(outs[band * LM_OUT_STRIDE + f]);
+    }
+  }
+  if (p.raw_tm16 != nullptr) {   // time-major: consecutive threads -> consecutive bands of one frame (192-byte rows)
+    __half* raw = p.raw_tm16 + (long(b) * p.T + t0) * LM_NMEL;
+    for (int i = tid; i < LM_NMEL * LM_FRAMES; i += LM_THREADS) {
+      const int f = i / LM_NMEL, band = i - f * LM_NMEL;
+      if (f < nfr) raw[long(f) * LM_NMEL + band] = __float2half_rn(outs[band * LM_OUT_STRIDE + f]);
+    }
   }
 }
 #endif  // !MB_HOST_EMULATION

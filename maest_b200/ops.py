@@ -70,6 +70,42 @@ def logmel(wav: torch.Tensor) -> torch.Tensor:
     return mel[0] if squeeze else mel
 
 
+def logmel_raw16(wav: torch.Tensor) -> torch.Tensor:
+    """[B, S] fp32 CUDA waveform -> [B, T, 96] fp16, un-normalised log10(1 + 1e4 mel), time-major: the layout of the
+    reference's .mmap training files (helpers/melspectrogram_extractor.py)."""
+    _need_cuda(wav)
+    w = wav.reshape(1, -1) if wav.dim() == 1 else wav
+    if w.dtype != torch.float32:
+        w = w.float()
+    if w.stride(-1) != 1:
+        w = w.contiguous()
+    B, S = w.shape
+    out = torch.empty((B, 1 + S // 256, 96), device=w.device, dtype=torch.float16)
+    with torch.cuda.device(w.device):
+        lib = _lib_for(w)
+        _lib.check(lib.maest_logmel_raw16_fwd(w.data_ptr(), B, S, w.stride(0), out.data_ptr(), _stream()), "logmel_raw16")
+    return out[0] if wav.dim() == 1 else out
+
+
+def mel_ingest(raw: torch.Tensor, frames_read: Optional[torch.Tensor] = None, roll_shift: Optional[torch.Tensor] = None,
+               norm_mean: Optional[float] = None, norm_std: Optional[float] = None) -> torch.Tensor:
+    """raw fp16 CUDA [B, T, 96] (file windows, time-major) -> [B, 1, 96, T] fp16: zero-pad centring, normalisation and time
+    roll of the reference's loader (discogs/dataset.py:120-139, discogs/datamodule.py:111-137) in one kernel."""
+    _need_cuda(raw, frames_read, roll_shift)
+    assert raw.dtype == torch.float16 and raw.dim() == 3 and raw.shape[2] == 96 and raw.is_contiguous()
+    B, T, _ = raw.shape
+    for t in (frames_read, roll_shift):
+        assert t is None or (t.dtype == torch.int32 and t.numel() == B and t.is_contiguous())
+    do_norm = norm_mean is not None
+    out = torch.empty((B, 1, 96, T), device=raw.device, dtype=torch.float16)
+    with torch.cuda.device(raw.device):
+        lib = _lib_for(raw)
+        _lib.check(lib.maest_mel_ingest_fwd(raw.data_ptr(), _p(frames_read), _p(roll_shift), B, T, int(do_norm),
+                                            float(norm_mean or 0.0), float(norm_std or 1.0), out.data_ptr(), _stream()),
+                   "mel_ingest")
+    return out
+
+
 def layernorm16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, op_dtype=F16,
                 save_stats: bool = False):
     _need_cuda(x, w, b)

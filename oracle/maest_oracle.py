@@ -97,7 +97,7 @@ def n_frames(samples: int) -> int:
     return 1 + samples // HOP
 
 
-def logmel(wave: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
+def logmel(wave: torch.Tensor, dtype=torch.float32, normalise: bool = True) -> torch.Tensor:
     """[..., S] waveform -> [..., 96, T] normalised log-mel, T = 1 + S // 256.
 
     models/helpers/melspectrogram.py:47-60.  Frame t = xp[256 t : 256 t + 512] of the waveform
@@ -118,6 +118,8 @@ def logmel(wave: torch.Tensor, dtype=torch.float32) -> torch.Tensor:
     power = spec.real ** 2 + spec.imag ** 2               # [B, T, 257]
     mel = power @ mel_filterbank(dtype)                   # [B, T, 96]
     out = torch.log10(1.0 + mel * 10000.0)
+    if not normalise:      # dataset-file flavour (helpers/melspectrogram_extractor.py): time-major, un-normalised
+        return out.reshape(*lead, T, N_MELS)
     out = (out - NORM_MEAN) / (NORM_STD * 2)
     return out.transpose(1, 2).reshape(*lead, N_MELS, T)
 
