@@ -270,6 +270,77 @@ def run_train(args):
         dist.destroy_process_group()
 
 
+def run_ingest(args):
+    """--mode ingest: one step = one training batch of raw float16 .mmap windows
+    (B clips x 1875 frames x 96 bands) -> [B, 1, 96, 1875] float16 model input.  `value`: kernel only, windows resident
+    in HBM; `e2e`: MelWindowBatcher from files on the box's disk (window reads + pinned H2D + kernel)."""
+    import tempfile
+    import numpy as np
+    import torch
+    from maest_b200 import ingest, ops
+    from oracle import ingest_oracle as IO
+
+    torch.cuda.set_device(0)
+    B, T = args.batch, 1875
+    rng = np.random.RandomState(0)
+    raw = torch.from_numpy((rng.rand(B, T, 96) * 5).astype(np.float16)).cuda()
+    nread = torch.full((B,), T, dtype=torch.int32, device="cuda")
+    shift = torch.from_numpy(rng.randint(-50, 51, B).astype(np.int32)).cuda()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")      # > 126 MB L2
+    for _ in range(max(args.warmup, 3)):
+        ops.mel_ingest(raw, nread, shift, ingest.NORM_MEAN, ingest.NORM_STD)
+    sampler = ClockSampler(0)
+    sampler.start()
+    ts = []
+    for _ in range(args.steps):
+        flush.zero_()
+        a, b = torch.cuda.Event(True), torch.cuda.Event(True)
+        a.record()
+        ops.mel_ingest(raw, nread, shift, ingest.NORM_MEAN, ingest.NORM_STD)
+        b.record()
+        torch.cuda.synchronize()
+        ts.append(a.elapsed_time(b))
+    ms = sum(ts) / len(ts)
+    with tempfile.TemporaryDirectory() as d:
+        files = []
+        for i in range(B):
+            f = os.path.join(d, f"{i}.mmap")
+            (rng.rand(4000, 96) * 5).astype(np.float16).tofile(f)
+            files.append(f)
+        bt = ingest.MelWindowBatcher(B, 30, roll=True)
+        for _ in range(3):
+            out = bt(files)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            out = bt(files)
+            out[0, 0, 0, 0].item()          # D2H read of the step's result
+        e2e_s = (time.perf_counter() - t0) / args.steps
+        clocks = sampler.stop()
+        # CPU baseline: the numpy restatement of the reference's loader on the same files, one thread (as a DataLoader worker would)
+        t0 = time.perf_counter()
+        n_cpu = min(B, 32)
+        for f in files[:n_cpu]:
+            whole = np.fromfile(f, dtype=np.float16).reshape(-1, 96)
+            IO.ingest(whole, T, 100, ingest.NORM_MEAN, ingest.NORM_STD, 7)
+        cpu_s = time.perf_counter() - t0
+    peaks = measured_peaks()
+    by = B * T * 96 * 2 * 2                      # algorithmic bytes: read the window once, write the batch once
+    line = dict(metric="clips/sec (loader ingest)", value=B / (ms / 1e3), unit="clips/s", n_gpus=1, steps=args.steps, warmup=max(args.warmup, 3),
+                ms_per_step=ms, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16", data="synthetic", mode="ingest",
+                config=dict(workload=f"raw float16 [frames,96] windows -> [{B},1,96,{T}] float16: zero-pad centring, transpose, fp16 normalisation, time roll",
+                            batch_per_gpu=B, l2="256 MB buffer zeroed between timed launches (L2 flush)"),
+                e2e=dict(value=B / e2e_s, unit="clips/s", h2d_bytes_per_step=B * T * 96 * 2 + 8 * B, d2h_bytes_per_step=2,
+                         note="MelWindowBatcher: np.memmap window reads into a pinned buffer + H2D + kernel, files on local disk (page cache warm)"),
+                gpu_launches=args.steps, clocks=clocks,
+                roofline=dict(bound="hbm", kernel="mel_ingest_kernel", achieved=by / (ms / 1e3) / 1e9, peak=peaks["hbm_gbs"], unit="GB/s",
+                              frac=by / (ms / 1e3) / 1e9 / peaks["hbm_gbs"], traffic=None, algorithmic_bytes_per_launch=by,
+                              peak_source=peaks["source"] + " hbm_gbs"),
+                cpu_baseline=dict(value=n_cpu / cpu_s, unit="clips/s", cores=1, kind="port",
+                                  sample=f"{n_cpu} clips, oracle/ingest_oracle.py (numpy restatement of discogs/dataset.py + datamodule norm/roll), one thread"))
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -284,8 +355,9 @@ def main():
     ap.add_argument("--cpu-baseline-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
-    ap.add_argument("--mode", default="infer", choices=["infer", "train"],
-                    help="infer: BASELINE.json configs[2] (headline).  train: configs[3], one optimisation step per 'step'")
+    ap.add_argument("--mode", default="infer", choices=["infer", "train", "ingest"],
+                    help="infer: BASELINE.json configs[2] (headline).  train: configs[3], one optimisation step per 'step'.  "
+                         "ingest: loader -> device ingest kernel (SURVEY.md section 8(f) row 1)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -293,6 +365,8 @@ def main():
         return run_reference(args)
     if args.mode == "train":
         return run_train(args)
+    if args.mode == "ingest":
+        return run_ingest(args)
 
     import torch
     import torch.distributed as dist
@@ -404,7 +478,7 @@ def main():
     clips = B * world * args.steps
     value = clips / (ms_dev / 1e3)
     e2e_val = clips / (ms_e2e / 1e3)
-    per_step_launches = 4 + DEPTH * 7
+    per_step_launches = 5 + DEPTH * 7      # logmel, pos table, patch gather, patch GEMM, 12 x (LN, qkv, attn, proj, LN, fc1, fc2), pool/head
     line = dict(metric="clips/sec", value=value, unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=args.op_dtype + " operands, fp32 accumulate/residual/softmax/mel", data="synthetic",

@@ -31,7 +31,12 @@ enum {
   MAEST_EPI_RESID32 = 2, /* out32 = resid32 + A W^T + bias                         (proj/fc2 + residual: :376,:206,:418-419) */
   MAEST_EPI_STORE32 = 3, /* out32 = A W^T + bias (+ addend table, + row remap)     (patch-embed + pos-embed: :250,:670-675) */
   MAEST_EPI_GELUBWD16 = 4, /* out16 = (A B^T) * gelu'(aux16)    (autograd of mlp.act + mlp.fc2, models/maest.py:204-206)           */
-  MAEST_EPI_ATOMIC32 = 5   /* out32 += A B^T (split-K, atomics)  (weight gradients; autograd of every nn.Linear / the conv)        */
+  MAEST_EPI_ATOMIC32 = 5,  /* out32 += A B^T (split-K, atomics)  (weight gradients; autograd of every nn.Linear / the conv)        */
+  /* LayerNorm folded into the GEMMs around it (maest_linear_ln_fwd; Block.forward, models/maest.py:418-419 with :395,:405):
+   *   LN(x) W^T + b  =  rstd * ((x*gamma) W^T)  -  rstd * mean * (W gamma)  +  (W beta + b)                                        */
+  MAEST_EPI_STORE16_LN = 7, /* consumer (qkv): A = x*gamma op16; out16 = rstd*acc - rstd*mean*ln_vec[n] + bias[n]                   */
+  MAEST_EPI_GELU16_LN = 8,  /* consumer (fc1): gelu_erf of the same                                                                 */
+  MAEST_EPI_RESID32_LN = 9  /* producer (proj, fc2): RESID32, plus out16b = x*ln_vec[n] (op16) and ln_stats[r] += (sum x, sum x^2) */
 };
 
 /* pooling modes (maest_pool_head_fwd) */
@@ -45,6 +50,9 @@ typedef struct MaestBlockWeights {
   const float* ln2_w; const float* ln2_b;      /* norm2.*                                         */
   const void* fc1_w;  const float* fc1_b;      /* mlp.fc1.weight op16 [3072,768], bias [3072]      */
   const void* fc2_w;  const float* fc2_b;      /* mlp.fc2.weight op16 [768,3072], bias [768]       */
+  /* optional (all four or none; NULL = every LayerNorm runs as its own kernel): vectors made by maest_ln_fold */
+  const float* qkv_wg; const float* qkv_bf;    /* qkv_w  . norm1.weight [2304];  qkv_b + qkv_w . norm1.bias [2304] */
+  const float* fc1_wg; const float* fc1_bf;    /* fc1_w  . norm2.weight [3072];  fc1_b + fc1_w . norm2.bias [3072] */
 } MaestBlockWeights;
 
 const char* maest_last_error(void);
@@ -125,6 +133,20 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
  * (cta_group::2, W tile shared by the two SMs of a TPC), 2 = per-shape choice (default).  Process-wide tuning switch;
  * results are identical. */
 int32_t maest_set_gemm_mode(int32_t pair_mode);
+
+/* LayerNorm folding, weight side (once per weight version): wg[n] = sum_k gamma[k] W[n,k], bf[n] = bias[n] + sum_k beta[k] W[n,k]
+ * from the 16-bit operand copy w16 [N, K] that the GEMM multiplies.  Replaces nothing by itself: it moves norm1 / norm2
+ * (models/maest.py:395,405) into the qkv / fc1 GEMM epilogues. */
+int32_t maest_ln_fold(const void* w16, const float* gamma, const float* beta, const float* bias, int32_t N, int32_t K,
+                      int32_t op_dtype, float* wg, float* bf, void* stream);
+
+/* Linear layers with the neighbouring LayerNorm folded in (epilogue = MAEST_EPI_*_LN).
+ *   producer (RESID32_LN): out32 = resid + A W^T + bias;  out16b = out32 * ln_vec (gamma of the next LayerNorm);
+ *                          ln_stats [M, 2] fp32 += (row sum, row sum of squares) -- the caller zeroes ln_stats first
+ *   consumer (STORE16_LN / GELU16_LN): A = the producer's out16b; ln_vec = wg, bias = bf from maest_ln_fold; ln_eps = LN epsilon */
+int32_t maest_linear_ln_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, int32_t M, int32_t N,
+                            int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out, const float* resid,
+                            float* ln_stats, const float* ln_vec, void* out16b, float ln_eps, void* stream);
 
 /* Fused multi-head attention, d_head 64.  Replaces Attention.forward lines models/maest.py:362-375.
  * qkv op16 [B*N, 3*H*64] as written by the qkv linear (columns = [q|k|v][head][64]); out op16 [B*N, H*64].

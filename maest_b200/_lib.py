@@ -15,13 +15,14 @@ c_void_p, c_int32, c_int64, c_size_t, c_float = C.c_void_p, C.c_int32, C.c_int64
 
 F16, BF16, F32 = 0, 1, 2
 EPI_STORE16, EPI_GELU16, EPI_RESID32, EPI_STORE32, EPI_GELUBWD16, EPI_ATOMIC32 = 0, 1, 2, 3, 4, 5
-ABI_VERSION = 3
+EPI_STORE16_LN, EPI_GELU16_LN, EPI_RESID32_LN = 7, 8, 9
+ABI_VERSION = 4
 HEAD_MEAN, HEAD_SEPARATED = 0, 1
 
 
 class MaestBlockWeights(C.Structure):
     _fields_ = [(n, c_void_p) for n in ("ln1_w", "ln1_b", "qkv_w", "qkv_b", "proj_w", "proj_b", "ln2_w", "ln2_b",
-                                        "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+                                        "fc1_w", "fc1_b", "fc2_w", "fc2_b", "qkv_wg", "qkv_bf", "fc1_wg", "fc1_bf")]
 
 
 # name -> (restype, argtypes); must list every symbol include/maest_b200.h declares
@@ -42,6 +43,9 @@ SIGNATURES = {
                                    c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p]),
     "maest_gemm": (c_int32, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int32, c_int32,
                              c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
+    "maest_ln_fold": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "maest_linear_ln_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
     "maest_set_gemm_mode": (c_int32, [c_int32]),
     "maest_attention_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "maest_attention_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -88,8 +88,9 @@ int g_gemm_pair_mode = 2;   // 0: 1-CTA tiles, 1: CTA-pair (cta_group::2) tiles,
 // Measured on B200 (M = 107 840): the pair kernel wins where the mainloop dominates (qkv 0.322 -> 0.312 ms, fc2 0.434 -> 0.400 ms)
 // and loses where the epilogue does (proj 0.188 -> 0.197 ms, fc1+GELU 0.524 -> 0.543 ms).
 inline bool use_pair_kernel(int epi, int K) {
+  if (epi == MAEST_EPI_GELU16_LN) return false;   // not instantiated for the pair kernel (the epilogue-bound shape)
   if (g_gemm_pair_mode != 2) return g_gemm_pair_mode == 1;
-  return epi == MAEST_EPI_STORE16 || (epi == MAEST_EPI_RESID32 && K >= 2048);
+  return epi == MAEST_EPI_STORE16 || epi == MAEST_EPI_STORE16_LN || ((epi == MAEST_EPI_RESID32 || epi == MAEST_EPI_RESID32_LN) && K >= 2048);
 }
 
 template <int DT, int EPI>
@@ -125,6 +126,8 @@ int launch_gemm_dt(int epi, bool a_mn, bool b_mn, const CUtensorMap& ta, const C
         return launch_gemm2<DT, EPI_GELU16>(ta, tb, p, st);
       case MAEST_EPI_RESID32: return launch_gemm2<DT, EPI_RESID32>(ta, tb, p, st);
       case MAEST_EPI_STORE32: return launch_gemm2<DT, EPI_STORE32>(ta, tb, p, st);
+      case MAEST_EPI_STORE16_LN: return launch_gemm2<DT, EPI_STORE16_LN>(ta, tb, p, st);
+      case MAEST_EPI_RESID32_LN: return launch_gemm2<DT, EPI_RESID32_LN>(ta, tb, p, st);
     }
   }
   if (!a_mn && !b_mn) {
@@ -135,6 +138,9 @@ int launch_gemm_dt(int epi, bool a_mn, bool b_mn, const CUtensorMap& ta, const C
         return launch_gemm<DT, EPI_GELU16, false, false>(ta, tb, p, st);
       case MAEST_EPI_RESID32: return launch_gemm<DT, EPI_RESID32, false, false>(ta, tb, p, st);
       case MAEST_EPI_STORE32: return launch_gemm<DT, EPI_STORE32, false, false>(ta, tb, p, st);
+      case MAEST_EPI_STORE16_LN: return launch_gemm<DT, EPI_STORE16_LN, false, false>(ta, tb, p, st);
+      case MAEST_EPI_GELU16_LN: return launch_gemm<DT, EPI_GELU16_LN, false, false>(ta, tb, p, st);
+      case MAEST_EPI_RESID32_LN: return launch_gemm<DT, EPI_RESID32_LN, false, false>(ta, tb, p, st);
     }
   } else if (!a_mn && b_mn) {
     switch (epi) {
@@ -171,6 +177,11 @@ int init_dt() {
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_GELU16_SAVE>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_RESID32>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_STORE32>, GEMM2_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm2_tn_kernel<DT, EPI_STORE16_LN>, GEMM2_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm2_tn_kernel<DT, EPI_RESID32_LN>, GEMM2_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE16_LN, false, false>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_GELU16_LN, false, false>, GEMM_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm_tn_kernel<DT, EPI_RESID32_LN, false, false>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, true>, att_smem_bytes<true>()))) return r;
   if ((r = set_smem(attention_fwd_spec_kernel<DT, 128>, 120 * 1024))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, false>, att_smem_bytes<false>()))) return r;
@@ -183,7 +194,7 @@ int init_dt() {
 extern "C" {
 
 const char* maest_last_error(void) { return g_err; }
-int32_t maest_abi_version(void) { return 3; }
+int32_t maest_abi_version(void) { return 4; }
 
 int32_t maest_init(int32_t device) {
   if (device < 0 || device >= 64) return fail(-1, "bad device %d", device);
@@ -273,6 +284,7 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = addend; p.ld_out = int(ld_out);
   p.aux16 = aux16; p.k_splits = k_splits;
+  p.ln_stats = nullptr; p.ln_vec = nullptr; p.out16b = nullptr; p.ln_eps = 0.f; p.ln_inv_n = 0.f;
   if (rows_per_group <= 0) { p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0; }
   else { p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; }
   if (epilogue == MAEST_EPI_RESID32 && !resid) return fail(-1, "gemm: RESID32 needs resid");
@@ -290,6 +302,42 @@ int32_t maest_linear_fwd(const void* a, int64_t lda, const void* w, int64_t ldw,
   if (epilogue < MAEST_EPI_STORE16 || epilogue > MAEST_EPI_STORE32) return fail(-1, "linear: unknown epilogue %d", epilogue);
   return maest_gemm(a, lda, 0, w, ldw, 0, bias, M, N, K, op_dtype, epilogue, out, ld_out, resid, addend, rows_per_group,
                     group_stride, row_offset, nullptr, 1, stream);
+}
+
+int32_t maest_ln_fold(const void* w16, const float* gamma, const float* beta, const float* bias, int32_t N, int32_t K,
+                      int32_t op_dtype, float* wg, float* bf, void* stream) {
+  if (N <= 0) return 0;
+  const int blocks = (N + 7) / 8;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (op_dtype == MAEST_BF16) ln_fold_kernel<DT_BF16><<<blocks, 256, 0, st>>>(w16, gamma, beta, bias, N, K, wg, bf);
+  else if (op_dtype == MAEST_F16) ln_fold_kernel<DT_F16><<<blocks, 256, 0, st>>>(w16, gamma, beta, bias, N, K, wg, bf);
+  else return fail(-1, "ln_fold: op_dtype must be f16/bf16");
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_linear_ln_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, int32_t M, int32_t N,
+                            int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out, const float* resid,
+                            float* ln_stats, const float* ln_vec, void* out16b, float ln_eps, void* stream) {
+  if (M <= 0 || N <= 0) return 0;
+  if (epilogue != MAEST_EPI_STORE16_LN && epilogue != MAEST_EPI_GELU16_LN && epilogue != MAEST_EPI_RESID32_LN)
+    return fail(-1, "linear_ln: epilogue %d is not a LayerNorm-folding epilogue", epilogue);
+  if (N % 32) return fail(-1, "linear_ln: N %% 32 must be 0");
+  if (op_dtype != MAEST_F16 && op_dtype != MAEST_BF16) return fail(-1, "linear_ln: op_dtype must be f16/bf16");
+  if (!ln_stats || !ln_vec) return fail(-1, "linear_ln: ln_stats / ln_vec are required");
+  if (epilogue == MAEST_EPI_RESID32_LN && (!resid || !out16b)) return fail(-1, "linear_ln: the producer epilogue needs resid and out16b");
+  CUtensorMap ta, tb;
+  int r;
+  if ((r = make_tmap(&ta, a, op_dtype, M, K, lda, GEMM_BM))) return r;
+  const bool pair_kernel = use_pair_kernel(epilogue, K);
+  if ((r = make_tmap(&tb, w, op_dtype, N, K, ldw, pair_kernel ? 128 : GEMM_BN))) return r;
+  GemmParams p;
+  p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = nullptr; p.ld_out = int(ld_out);
+  p.aux16 = nullptr; p.k_splits = 1; p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0;
+  p.ln_stats = ln_stats; p.ln_vec = ln_vec; p.out16b = out16b; p.ln_eps = ln_eps; p.ln_inv_n = 1.0f / float(K);
+  cudaStream_t st = (cudaStream_t)stream;
+  return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, false, false, ta, tb, p, st)
+                                : launch_gemm_dt<DT_F16>(epilogue, false, false, ta, tb, p, st);
 }
 
 int32_t maest_layernorm_fwd(const float* x, const float* w, const float* b, void* y16, int32_t op_dtype, int32_t rows,
@@ -389,8 +437,8 @@ int32_t maest_patch_tokens_fwd(const void* mel, int32_t mel_dtype, int32_t B, in
 }
 
 size_t maest_encoder_workspace_bytes(int64_t rows) {
-  // h16 [rows,768] | qkv16 [rows,2304] | o16 [rows,768] | u16 [rows,3072]  (+ 128 rows of slack per buffer)
-  return size_t(rows + 128) * (768 + 2304 + 768 + 3072) * 2 + 1024;
+  // h16 [rows,768] | qkv16 [rows,2304] | o16 [rows,768] | u16 [rows,3072]  (+ 128 rows of slack per buffer) | LN stats [rows,2] fp32
+  return size_t(rows + 128) * (768 + 2304 + 768 + 3072) * 2 + size_t(rows + 128) * 8 + 1024;
 }
 
 int32_t maest_encoder_fwd(float* x, int32_t B, int32_t N, const MaestBlockWeights* blocks, int32_t n_blocks,
@@ -405,25 +453,55 @@ int32_t maest_encoder_fwd(float* x, int32_t B, int32_t N, const MaestBlockWeight
   uint8_t* qkv16 = h16 + R * 768 * 2;
   uint8_t* o16 = qkv16 + R * 2304 * 2;
   uint8_t* u16 = o16 + R * 768 * 2;
+  float* stats = reinterpret_cast<float*>(u16 + R * 3072 * 2);
   int r;
+  // LayerNorm folding (23 of the 24 LayerNorms disappear into the GEMM epilogues around them) needs the folded vectors of
+  // every block; block 0's norm1 reads the token buffer written by K2 and stays a kernel.
+  bool fold = true;
+  for (int i = 0; i < n_blocks; ++i) fold = fold && blocks[i].qkv_wg && blocks[i].qkv_bf && blocks[i].fc1_wg && blocks[i].fc1_bf;
+  cudaStream_t st = (cudaStream_t)stream;
+  bool h16_is_folded = false;   // h16 holds x * gamma of the next LayerNorm and `stats` its row sums
   for (int i = 0; i < n_blocks; ++i) {
     const MaestBlockWeights& w = blocks[i];
     const bool attn_only = last_attn_only && i == n_blocks - 1;
-    if ((r = maest_layernorm_fwd(x, w.ln1_w, w.ln1_b, h16, op_dtype, int(M), 1e-6f, nullptr, nullptr, stream))) return r;
-    if ((r = maest_linear_fwd(h16, 768, w.qkv_w, 768, w.qkv_b, int(M), 2304, 768, op_dtype, MAEST_EPI_STORE16, qkv16, 2304,
-                              nullptr, nullptr, 0, 0, 0, stream))) return r;
+    if (h16_is_folded) {
+      if ((r = maest_linear_ln_fwd(h16, 768, w.qkv_w, 768, w.qkv_bf, int(M), 2304, 768, op_dtype, MAEST_EPI_STORE16_LN, qkv16, 2304,
+                                   nullptr, stats, w.qkv_wg, nullptr, 1e-6f, stream))) return r;
+    } else {
+      if ((r = maest_layernorm_fwd(x, w.ln1_w, w.ln1_b, h16, op_dtype, int(M), 1e-6f, nullptr, nullptr, stream))) return r;
+      if ((r = maest_linear_fwd(h16, 768, w.qkv_w, 768, w.qkv_b, int(M), 2304, 768, op_dtype, MAEST_EPI_STORE16, qkv16, 2304,
+                                nullptr, nullptr, 0, 0, 0, stream))) return r;
+    }
+    h16_is_folded = false;
     if ((r = maest_attention_fwd(qkv16, o16, nullptr, B, N, 12, op_dtype, attn_variant, stream))) return r;
     if (attn_only) {
       return maest_linear_fwd(o16, 768, w.proj_w, 768, w.proj_b, int(M), 768, 768, op_dtype, MAEST_EPI_STORE32, x, 768, nullptr,
                               nullptr, 0, 0, 0, stream);
     }
-    if ((r = maest_linear_fwd(o16, 768, w.proj_w, 768, w.proj_b, int(M), 768, 768, op_dtype, MAEST_EPI_RESID32, x, 768, x,
-                              nullptr, 0, 0, 0, stream))) return r;
-    if ((r = maest_layernorm_fwd(x, w.ln2_w, w.ln2_b, h16, op_dtype, int(M), 1e-6f, nullptr, nullptr, stream))) return r;
-    if ((r = maest_linear_fwd(h16, 768, w.fc1_w, 768, w.fc1_b, int(M), 3072, 768, op_dtype, MAEST_EPI_GELU16, u16, 3072, nullptr,
-                              nullptr, 0, 0, 0, stream))) return r;
-    if ((r = maest_linear_fwd(u16, 3072, w.fc2_w, 3072, w.fc2_b, int(M), 768, 3072, op_dtype, MAEST_EPI_RESID32, x, 768, x,
-                              nullptr, 0, 0, 0, stream))) return r;
+    if (fold) {
+      // x += proj(o) and, in the same epilogue, h16 = x * gamma2 and stats = (sum x, sum x^2); fc1 finishes norm2
+      CUDA_OK(cudaMemsetAsync(stats, 0, size_t(M) * 8, st));
+      if ((r = maest_linear_ln_fwd(o16, 768, w.proj_w, 768, w.proj_b, int(M), 768, 768, op_dtype, MAEST_EPI_RESID32_LN, x, 768, x,
+                                   stats, w.ln2_w, h16, 0.f, stream))) return r;
+      if ((r = maest_linear_ln_fwd(h16, 768, w.fc1_w, 768, w.fc1_bf, int(M), 3072, 768, op_dtype, MAEST_EPI_GELU16_LN, u16, 3072,
+                                   nullptr, stats, w.fc1_wg, nullptr, 1e-6f, stream))) return r;
+    } else {
+      if ((r = maest_linear_fwd(o16, 768, w.proj_w, 768, w.proj_b, int(M), 768, 768, op_dtype, MAEST_EPI_RESID32, x, 768, x,
+                                nullptr, 0, 0, 0, stream))) return r;
+      if ((r = maest_layernorm_fwd(x, w.ln2_w, w.ln2_b, h16, op_dtype, int(M), 1e-6f, nullptr, nullptr, stream))) return r;
+      if ((r = maest_linear_fwd(h16, 768, w.fc1_w, 768, w.fc1_b, int(M), 3072, 768, op_dtype, MAEST_EPI_GELU16, u16, 3072, nullptr,
+                                nullptr, 0, 0, 0, stream))) return r;
+    }
+    if (fold && i + 1 < n_blocks) {
+      // x += fc2(u) producing the operand and statistics of the NEXT block's norm1
+      CUDA_OK(cudaMemsetAsync(stats, 0, size_t(M) * 8, st));
+      if ((r = maest_linear_ln_fwd(u16, 3072, w.fc2_w, 3072, w.fc2_b, int(M), 768, 3072, op_dtype, MAEST_EPI_RESID32_LN, x, 768, x,
+                                   stats, blocks[i + 1].ln1_w, h16, 0.f, stream))) return r;
+      h16_is_folded = true;
+    } else {
+      if ((r = maest_linear_fwd(u16, 3072, w.fc2_w, 3072, w.fc2_b, int(M), 768, 3072, op_dtype, MAEST_EPI_RESID32, x, 768, x,
+                                nullptr, 0, 0, 0, stream))) return r;
+    }
   }
   return 0;
 }

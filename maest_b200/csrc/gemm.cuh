@@ -34,6 +34,12 @@ enum : int {
   EPI_GELUBWD16 = 4,  // out16[r,n] = acc * gelu'(aux16[r,n])                (fc2 dgrad fused with the GELU backward)
   EPI_ATOMIC32 = 5,   // out32[r,n] += acc  (red.global.add.f32; split-K weight gradients accumulate into .grad)
   EPI_GELU16_SAVE = 6,  // EPI_GELU16 that also stores the pre-activation to aux16 (training forward)
+  // LayerNorm folded into the GEMMs around it (inference): the PRODUCER of the residual stream also emits the 16-bit operand
+  // xg = x * gamma_next and the per-row sum / sum of squares of x; the CONSUMER multiplies xg by the un-normalised weight and
+  // finishes the normalisation per output element:  LN(x) W^T + b = rstd (xg W^T) - rstd mean (W gamma) + (W beta + b).
+  EPI_STORE16_LN = 7,   // consumer: out16[r,n] = rstd_r * acc - rstd_r * mean_r * ln_vec[n] + bias[n]            (qkv)
+  EPI_GELU16_LN = 8,    // consumer: out16[r,n] = gelu_erf(same)                                                   (fc1)
+  EPI_RESID32_LN = 9,   // producer: EPI_RESID32, plus out16b[r,n] = x * ln_vec[n] and ln_stats[r] += (sum x, sum x^2) (proj, fc2)
 };
 
 struct GemmParams {
@@ -46,6 +52,11 @@ struct GemmParams {
                          // EPI_GELUBWD16: input, the saved pre-activation.  Same shape / row stride as out.
   int ld_out;
   int k_splits;          // >1: the K loop is split across CTAs (use with EPI_ATOMIC32)
+  // LayerNorm folding (EPI_*_LN)
+  float* ln_stats;       // [rows][2] fp32: sum x, sum x^2 over the 768 features (producer: red.add; consumer: read)
+  const float* ln_vec;   // consumer: W gamma [N];  producer: gamma of the LayerNorm that follows [N]
+  void* out16b;          // producer: second output, x * gamma as op16, same shape / row stride as out
+  float ln_eps, ln_inv_n;  // consumer: epsilon and 1 / (features per row)
   // output row remap:  r = (m / rows_per_group) * group_stride + row_offset + (m % rows_per_group)
   int rows_per_group, group_stride, row_offset;
 };
@@ -131,7 +142,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
   float4 xr[8];
   uint2 ar[8];   // GELUBWD16: the saved pre-activation tile, prefetched the same way
   auto load_resid = [&](int cc) {
-    if constexpr (EPI == EPI_RESID32) {
+    if constexpr (EPI == EPI_RESID32 || EPI == EPI_RESID32_LN) {
       const int col = n0 + cc * 32 + c4 * 4;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
@@ -156,6 +167,22 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
       }
     }
   };
+  constexpr bool kLnConsumer = (EPI == EPI_STORE16_LN || EPI == EPI_GELU16_LN);
+  constexpr bool kLnProducer = (EPI == EPI_RESID32_LN);
+  float ln_r[kLnConsumer ? 8 : 1], ln_mr[kLnConsumer ? 8 : 1];   // rstd and -mean * rstd of this thread's 8 rows
+  if constexpr (kLnConsumer) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      ln_r[i] = 0.f; ln_mr[i] = 0.f;
+      if (row_ok(i)) {
+        const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * out_row(i));
+        const float mean = st.x * p.ln_inv_n;
+        const float var = fmaxf(fmaf(st.y, p.ln_inv_n, -mean * mean), 0.f);
+        ln_r[i] = rsqrtf(var + p.ln_eps);
+        ln_mr[i] = -mean * ln_r[i];
+      }
+    }
+  }
   load_resid(0);
   mbar_wait(tfull, aphase);
   tc_fence_after();
@@ -183,23 +210,50 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
     const int col = n + c4 * 4;
     float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (kLnConsumer || kLnProducer) g4 = __ldg(reinterpret_cast<const float4*>(p.ln_vec + col));
     float4 acc4[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rl = i * 4 + sub_row;
       float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
-      a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
-      if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
+      if constexpr (kLnConsumer) {   // finish the LayerNorm: rstd * acc - rstd * mean * (W gamma) + (W beta + b)
+        a.x = fmaf(a.x, ln_r[i], fmaf(ln_mr[i], g4.x, b4.x)); a.y = fmaf(a.y, ln_r[i], fmaf(ln_mr[i], g4.y, b4.y));
+        a.z = fmaf(a.z, ln_r[i], fmaf(ln_mr[i], g4.z, b4.z)); a.w = fmaf(a.w, ln_r[i], fmaf(ln_mr[i], g4.w, b4.w));
+      } else {
+        a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+      }
+      if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
       acc4[i] = a;
     }
-    if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32) load_resid(cc + 1);   // next chunk's residual / table rows are in flight during the stores
+    if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) load_resid(cc + 1);   // next chunk's residual / table rows are in flight during the stores
+    if constexpr (kLnProducer) {
+      // row statistics of the new residual stream: reduce the 4-column partials over the 8 lanes that share a row, one
+      // red.add pair per row and 32-column chunk.  All lanes take part in the shuffles (rows beyond M contribute zeros).
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 a = acc4[i];
+        const bool ok = row_ok(i);
+        float s1 = ok ? (a.x + a.y) + (a.z + a.w) : 0.f;
+        float s2 = ok ? fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w))) : 0.f;
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        }
+        if (ok && c4 == 0) {
+          atomicAdd(p.ln_stats + 2 * out_row(i), s1);
+          atomicAdd(p.ln_stats + 2 * out_row(i) + 1, s2);
+        }
+      }
+    }
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 a = acc4[i];
       if (!row_ok(i)) continue;
       const long r = out_row(i);
-      if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELUBWD16) {
-        if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE) {
+      if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELUBWD16 || kLnConsumer) {
+        if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELU16_LN) {
           if constexpr (EPI == EPI_GELU16_SAVE) {   // training: keep the pre-activation for the backward pass
             uint2 pre;
             pre.x = O::pack(a.x, a.y);
@@ -223,6 +277,12 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
         atomicAdd(dst, a.x); atomicAdd(dst + 1, a.y); atomicAdd(dst + 2, a.z); atomicAdd(dst + 3, a.w);
       } else if constexpr (EPI == EPI_RESID32) {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
+      } else if constexpr (kLnProducer) {
+        *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
+        uint2 o;
+        o.x = O::pack(a.x * g4.x, a.y * g4.y);
+        o.y = O::pack(a.z * g4.z, a.w * g4.w);
+        *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.out16b) + r * p.ld_out + col) = o;
       } else {
         *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + r * p.ld_out + col) = a;
       }

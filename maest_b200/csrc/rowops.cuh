@@ -46,6 +46,29 @@ __global__ void __launch_bounds__(256) layernorm_to16_kernel(const float* __rest
   }
 }
 
+// LayerNorm folding, weight side (done once per weight version): for the Linear that follows a LayerNorm(gamma, beta),
+//   wg[n] = sum_k gamma[k] W16[n,k]      bf[n] = bias[n] + sum_k beta[k] W16[n,k]
+// computed from the 16-bit operand copy the GEMM really multiplies.  One warp per output feature n.
+template <int DT>
+__global__ void __launch_bounds__(256) ln_fold_kernel(const void* __restrict__ w16, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, const float* __restrict__ bias, int N, int K,
+                                                      float* __restrict__ wg, float* __restrict__ bf) {
+  using O = Op16<DT>;
+  const int n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (n >= N) return;
+  const typename O::T* w = reinterpret_cast<const typename O::T*>(w16) + long(n) * K;
+  float a = 0.f, b = 0.f;
+  for (int k = lane; k < K; k += 32) {
+    const float wv = O::to_f(w[k]);
+    a = fmaf(gamma[k], wv, a);
+    b = fmaf(beta[k], wv, b);
+  }
+  a = warp_sum(a);
+  b = warp_sum(b);
+  if (lane == 0) { wg[n] = a; bf[n] = (bias ? bias[n] : 0.f) + b; }
+}
+
 // emb[b, 0:768] = x[b,0], emb[b,768:1536] = x[b,1], emb[b,1536:2304] = mean(x[b,2:])   models/maest.py:825-829
 // grid (B, 768/64), 256 threads = 4 row-groups x 64 columns
 __global__ void __launch_bounds__(256) block_embedding_kernel(const float* __restrict__ x, int N, float* __restrict__ emb) {

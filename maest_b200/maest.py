@@ -196,12 +196,16 @@ def trunc_normal_(t, std=0.02):
     return nn.init.trunc_normal_(t, mean=0.0, std=std, a=-2.0, b=2.0)   # vit_helpers.py:110-166 semantics
 
 
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
 class MAEST(nn.Module):
     def __init__(self, u_patchout=0, s_patchout_t=0, s_patchout_f=0, s_patchout_f_indices=(),
                  s_patchout_f_interleaved=0, s_patchout_t_indices=(), s_patchout_t_interleaved=0,
                  img_size=(96, 1875), patch_size=16, stride=(10, 10), in_chans=1, num_classes=400,
                  embed_dim=EMBED, depth=DEPTH, num_heads=HEADS, distilled=True, distilled_type="mean",
-                 op_dtype="fp16", attn_variant=0):
+                 op_dtype="fp16", attn_variant=0, fuse_ln=True):
         super().__init__()
         if embed_dim != EMBED or num_heads != HEADS or patch_size != PATCH or in_chans != 1 or not distilled:
             raise NotImplementedError("the B200 path is specialised to ViT-Base/16, 12 heads, mono, distilled (all shipped MAEST configs)")
@@ -221,6 +225,7 @@ class MAEST(nn.Module):
         self.distilled_type = distilled_type
         self.op_dtype = op_dtype          # 16-bit GEMM operand type: "fp16" (default, tighter parity) or "bf16"
         self.attn_variant = attn_variant
+        self.fuse_ln = fuse_ln       # inference: fold norm1 / norm2 into the GEMM epilogues around them (23 of 24 LayerNorm launches)
         if num_classes == 400:
             self.labels = discogs_400labels
         elif num_classes == 519:
@@ -297,6 +302,17 @@ class MAEST(nn.Module):
             t = t.float()
         return t.contiguous()
 
+    def _ln_fold(self, name: str, w16: torch.Tensor, ln: nn.LayerNorm, bias: torch.Tensor):
+        """(W gamma, bias + W beta) for the Linear that follows `ln`; re-made when any of the four tensors changes."""
+        key = ("fold", name, w16.dtype)
+        ver = (w16.data_ptr(), ln.weight._version, ln.weight.data_ptr(), ln.bias._version, ln.bias.data_ptr(), bias._version, bias.data_ptr())
+        hit = self._w16.get(key)
+        if hit is None or hit[0] != ver:
+            hit = (ver, ops.ln_fold(w16, self._f32(ln.weight), self._f32(ln.bias), self._f32(bias)))
+            self._w16[key] = hit
+            self._block_table = None
+        return hit[1]
+
     def _blocks_ctypes(self):
         """MaestBlockWeights[depth] with current device pointers (rebuilt if any parameter was re-staged/moved)."""
         sig = []
@@ -308,11 +324,17 @@ class MAEST(nn.Module):
             f32 = [self._f32(p) for p in (blk.norm1.weight, blk.norm1.bias, blk.attn.qkv.bias, blk.attn.proj.bias,
                                           blk.norm2.weight, blk.norm2.bias, blk.mlp.fc1.bias, blk.mlp.fc2.bias)]
             keep += w16 + f32
+            fold = [None] * 4
+            if self.fuse_ln:
+                fold = list(self._ln_fold(f"blocks.{i}.qkv", w16[0], blk.norm1, blk.attn.qkv.bias)) + \
+                    list(self._ln_fold(f"blocks.{i}.fc1", w16[2], blk.norm2, blk.mlp.fc1.bias))
+                keep += fold
             rows.append(_lib.MaestBlockWeights(
                 ln1_w=f32[0].data_ptr(), ln1_b=f32[1].data_ptr(), qkv_w=w16[0].data_ptr(), qkv_b=f32[2].data_ptr(),
                 proj_w=w16[1].data_ptr(), proj_b=f32[3].data_ptr(), ln2_w=f32[4].data_ptr(), ln2_b=f32[5].data_ptr(),
-                fc1_w=w16[2].data_ptr(), fc1_b=f32[6].data_ptr(), fc2_w=w16[3].data_ptr(), fc2_b=f32[7].data_ptr()))
-            sig += [t.data_ptr() for t in w16 + f32]
+                fc1_w=w16[2].data_ptr(), fc1_b=f32[6].data_ptr(), fc2_w=w16[3].data_ptr(), fc2_b=f32[7].data_ptr(),
+                qkv_wg=_ptr(fold[0]), qkv_bf=_ptr(fold[1]), fc1_wg=_ptr(fold[2]), fc1_bf=_ptr(fold[3])))
+            sig += [t.data_ptr() for t in w16 + f32] + [_ptr(t) for t in fold]
         sig = tuple(sig)
         if self._block_table is None or self._block_table[0] != sig:
             arr = (_lib.MaestBlockWeights * len(rows))(*rows)
@@ -506,8 +528,8 @@ def get_maest(arch, pretrained: bool = True, n_classes: int = 400, in_channels: 
               s_patchout_f: int = 0, s_patchout_f_indices: tuple = (), s_patchout_f_interleaved: int = 0,
               s_patchout_t_indices: tuple = (), s_patchout_t_interleaved: int = 0, distilled_type: str = "mean",
               checkpoint: str = None, checkpoint_swa_weigts: bool = True, checkpoint_discard_head: bool = False,
-              op_dtype: str = "fp16"):
-    """Same signature / defaults / arch table as the reference (`op_dtype` is the only addition)."""
+              op_dtype: str = "fp16", fuse_ln: bool = True):
+    """Same signature / defaults / arch table as the reference (`op_dtype` and `fuse_ln` are the only additions)."""
     if arch not in _ARCH_DEFAULT_T:
         raise NotImplementedError(f"model {arch} not implemented")        # models/maest.py:1530
     if not input_t:
@@ -525,7 +547,7 @@ def get_maest(arch, pretrained: bool = True, n_classes: int = 400, in_channels: 
                   s_patchout_f_indices=s_patchout_f_indices, s_patchout_f_interleaved=s_patchout_f_interleaved,
                   s_patchout_t_indices=s_patchout_t_indices, s_patchout_t_interleaved=s_patchout_t_interleaved,
                   img_size=(input_f, input_t), stride=stride, in_chans=in_channels, num_classes=n_classes,
-                  distilled_type=distilled_type, op_dtype=op_dtype)
+                  distilled_type=distilled_type, op_dtype=op_dtype, fuse_ln=fuse_ln)
     if checkpoint:
         state_dict = torch.load(checkpoint, map_location="cpu")["state_dict"]
         replace_str = "net_swa." if checkpoint_swa_weigts else ""

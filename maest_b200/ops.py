@@ -148,6 +148,37 @@ def linear(a: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], epilo
     return out
 
 
+def ln_fold(w16: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Optional[torch.Tensor]):
+    """Weight-side half of the LayerNorm folding: (W gamma, bias + W beta) as fp32 [N] vectors from the 16-bit weight copy."""
+    _need_cuda(w16, gamma, beta, bias)
+    N, K = w16.shape
+    assert w16.is_contiguous() and gamma.numel() == K and beta.numel() == K
+    wg = torch.empty(N, device=w16.device, dtype=torch.float32)
+    bf = torch.empty(N, device=w16.device, dtype=torch.float32)
+    with torch.cuda.device(w16.device):
+        lib = _lib_for(w16)
+        _lib.check(lib.maest_ln_fold(w16.data_ptr(), gamma.data_ptr(), beta.data_ptr(), _p(bias), N, K, _TORCH2DT[w16.dtype],
+                                     wg.data_ptr(), bf.data_ptr(), _stream()), "ln_fold")
+    return wg, bf
+
+
+def linear_ln(a: torch.Tensor, w16: torch.Tensor, bias: torch.Tensor, epilogue: int, ln_stats: torch.Tensor, ln_vec: torch.Tensor,
+              out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, out16b: Optional[torch.Tensor] = None,
+              eps: float = 1e-6) -> torch.Tensor:
+    """Linear with the neighbouring LayerNorm folded in (include/maest_b200.h: maest_linear_ln_fwd)."""
+    _need_cuda(a, w16, bias, ln_stats, ln_vec, out, resid, out16b)
+    M, K = a.shape
+    N = w16.shape[0]
+    if out is None:
+        out = torch.empty((M, N), device=a.device, dtype=torch.float32 if epilogue == _lib.EPI_RESID32_LN else a.dtype)
+    with torch.cuda.device(a.device):
+        lib = _lib_for(a)
+        _lib.check(lib.maest_linear_ln_fwd(a.data_ptr(), a.stride(0), w16.data_ptr(), w16.stride(0), _p(bias), M, N, K, _TORCH2DT[a.dtype],
+                                           epilogue, out.data_ptr(), out.stride(0), _p(resid), ln_stats.data_ptr(), ln_vec.data_ptr(),
+                                           _p(out16b), float(eps), _stream()), "linear_ln")
+    return out
+
+
 def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 0, save_lse: bool = False):
     """qkv [B*N, 3*heads*64] 16-bit -> o [B*N, heads*64] 16-bit (and, for training, lse fp32 [B, heads, N])."""
     _need_cuda(qkv)

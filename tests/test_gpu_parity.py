@@ -45,7 +45,7 @@ def m30():
 
 def test_native_library_is_loaded():
     lib = _lib.init(0)
-    assert lib.maest_abi_version() == 3
+    assert lib.maest_abi_version() == 4
     maps = open("/proc/self/maps").read()
     assert "libmaest_b200.so" in maps
 
@@ -247,6 +247,48 @@ def test_bf16_operands_vs_reference(golden):
     with torch.no_grad():
         lo, em = m(synth.wave_a(2, 160000).cuda())
     assert rel(lo, g["logits"]) < TOL_BF16 and rel(em, g["emb"]) < TOL_BF16
+
+
+def test_layernorm_folding_units():
+    """Producer / consumer epilogues of the LayerNorm folding against float64 math (models/maest.py:418-419 with :395,:405)."""
+    g = torch.Generator().manual_seed(21)
+    M, D, N2 = 300, 768, 2304
+    x0 = (torch.randn(M, D, generator=g) * 2 + 0.7).cuda()                 # residual stream with a non-zero row mean
+    a = (torch.randn(M, D, generator=g) * 0.5).half().cuda()
+    wp = (torch.randn(D, D, generator=g) * 0.04).half().cuda()
+    bp = torch.randn(D, generator=g).cuda() * 0.1
+    gamma, beta = (1 + 0.3 * torch.randn(D, generator=g)).cuda(), (0.2 * torch.randn(D, generator=g)).cuda()
+    w2 = (torch.randn(N2, D, generator=g) * 0.04).half().cuda()
+    b2 = torch.randn(N2, generator=g).cuda() * 0.1
+    stats = torch.zeros(M, 2, device="cuda")
+    h16 = torch.empty(M, D, device="cuda", dtype=torch.float16)
+    x1 = ops.linear_ln(a, wp, bp, _lib.EPI_RESID32_LN, stats, gamma, resid=x0, out16b=h16)
+    ref_x1 = x0.double() + a.double() @ wp.double().t() + bp.double()
+    assert rel(x1, ref_x1) < 1e-6
+    assert rel(stats[:, 0], ref_x1.sum(1)) < 1e-5 and rel(stats[:, 1], (ref_x1 ** 2).sum(1)) < 1e-5
+    assert rel(h16, ref_x1 * gamma.double()) < 4e-4
+    wg, bf = ops.ln_fold(w2, gamma, beta, b2)
+    assert rel(wg, w2.double() @ gamma.double()) < 1e-6 and rel(bf, b2.double() + w2.double() @ beta.double()) < 1e-6
+    ref_ln = torch.nn.functional.layer_norm(ref_x1, (D,), gamma.double(), beta.double(), 1e-6)
+    y = ops.linear_ln(h16, w2, bf, _lib.EPI_STORE16_LN, stats, wg)
+    assert rel(y, ref_ln @ w2.double().t() + b2.double()) < 1e-3
+    y = ops.linear_ln(h16, w2, bf, _lib.EPI_GELU16_LN, stats, wg)
+    assert rel(y, torch.nn.functional.gelu(ref_ln @ w2.double().t() + b2.double())) < 1e-3
+
+
+def test_unfused_layernorm_path_vs_reference(golden):
+    """fuse_ln=False keeps every LayerNorm as its own kernel (the training forward uses that form); both must match the reference."""
+    g = golden["c2"]
+    m = make("discogs-maest-10s-pw-129e", 62, fuse_ln=False)
+    with torch.no_grad():
+        lo, em = m(synth.wave_a(2, 160000).cuda())
+        e6 = m(synth.wave_a(2, 160000).cuda(), transformer_block=6)[1]
+    assert rel(lo, g["logits"]) < TOL_F16 and rel(em, g["emb"]) < TOL_F16
+    m2 = make("discogs-maest-10s-pw-129e", 62)
+    with torch.no_grad():
+        lo2, _ = m2(synth.wave_a(2, 160000).cuda())
+        e62 = m2(synth.wave_a(2, 160000).cuda(), transformer_block=6)[1]
+    assert rel(lo2, lo) < 5e-4 and rel(e62, e6) < 5e-4
 
 
 def test_attention_variants_agree(m10):
