@@ -167,17 +167,39 @@ def kernel_breakdown(model, wav, iters: int = 2):
         tok = timed("patch_tokens", lambda: model.tokens_from_mel(mel))
         B, N, _ = tok.shape
         x = tok.view(B * N, EMBED)
+        fuse = bool(getattr(model, "fuse_ln", False))
+        nb = len(model.blocks)
+        stats = parts = None
+        if fuse:
+            parts = torch.empty((EMBED // 32, B * N, 4), device=x.device, dtype=torch.float32)
+        h = None
         for i, blk in enumerate(model.blocks):
             w = {k: model._weight16(f"blocks.{i}.{k}", p) for k, p in (("qkv", blk.attn.qkv.weight), ("proj", blk.attn.proj.weight),
                                                                        ("fc1", blk.mlp.fc1.weight), ("fc2", blk.mlp.fc2.weight))}
-            h = timed("layernorm", lambda: ops.layernorm16(x, blk.norm1.weight.detach(), blk.norm1.bias.detach(), 1e-6, dt))
-            qkv = timed("gemm_qkv", lambda: ops.linear(h, w["qkv"], blk.attn.qkv.bias.detach(), _lib.EPI_STORE16))
+            if fuse and i > 0:      # norm1 was folded into the previous block's fc2 epilogue (h, stats) and finishes in this one
+                wg, bf = model._ln_fold(f"blocks.{i}.qkv", w["qkv"], blk.norm1, blk.attn.qkv.bias)
+                qkv = timed("gemm_qkv", lambda: ops.linear_ln(h, w["qkv"], bf, _lib.EPI_STORE16_LN, stats, wg))
+            else:
+                h = timed("layernorm", lambda: ops.layernorm16(x, blk.norm1.weight.detach(), blk.norm1.bias.detach(), 1e-6, dt))
+                qkv = timed("gemm_qkv", lambda: ops.linear(h, w["qkv"], blk.attn.qkv.bias.detach(), _lib.EPI_STORE16))
             o = timed("attention", lambda: ops.attention(qkv, B, N, HEADS, model.attn_variant))
-            timed("gemm_proj", lambda: ops.linear(o, w["proj"], blk.attn.proj.bias.detach(), _lib.EPI_RESID32, resid=x, out=x))
-            h = timed("layernorm", lambda: ops.layernorm16(x, blk.norm2.weight.detach(), blk.norm2.bias.detach(), 1e-6, dt))
-            u = timed("gemm_fc1", lambda: ops.linear(h, w["fc1"], blk.mlp.fc1.bias.detach(), _lib.EPI_GELU16))
-            timed("gemm_fc2", lambda: ops.linear(u, w["fc2"], blk.mlp.fc2.bias.detach(), _lib.EPI_RESID32, resid=x, out=x))
-            del h, qkv, o, u
+            if fuse:
+                wg, bf = model._ln_fold(f"blocks.{i}.fc1", w["fc1"], blk.norm2, blk.mlp.fc1.bias)
+                timed("gemm_proj", lambda: ops.linear_ln(o, w["proj"], blk.attn.proj.bias.detach(), _lib.EPI_RESID32_LN, parts, blk.norm2.weight.detach(),
+                                                         out=x, resid=x, out16b=h))
+                stats = timed("layernorm", lambda: ops.ln_finalize(parts))
+                u = timed("gemm_fc1", lambda: ops.linear_ln(h, w["fc1"], bf, _lib.EPI_GELU16_LN, stats, wg))
+            else:
+                timed("gemm_proj", lambda: ops.linear(o, w["proj"], blk.attn.proj.bias.detach(), _lib.EPI_RESID32, resid=x, out=x))
+                h = timed("layernorm", lambda: ops.layernorm16(x, blk.norm2.weight.detach(), blk.norm2.bias.detach(), 1e-6, dt))
+                u = timed("gemm_fc1", lambda: ops.linear(h, w["fc1"], blk.mlp.fc1.bias.detach(), _lib.EPI_GELU16))
+            if fuse and i + 1 < nb:
+                timed("gemm_fc2", lambda: ops.linear_ln(u, w["fc2"], blk.mlp.fc2.bias.detach(), _lib.EPI_RESID32_LN, parts,
+                                                        model.blocks[i + 1].norm1.weight.detach(), out=x, resid=x, out16b=h))
+                stats = timed("layernorm", lambda: ops.ln_finalize(parts))
+            else:
+                timed("gemm_fc2", lambda: ops.linear(u, w["fc2"], blk.mlp.fc2.bias.detach(), _lib.EPI_RESID32, resid=x, out=x))
+            del qkv, o, u
         timed("pool_head", lambda: ops.pool_head(tok, B, N, model.norm.weight.detach(), model.norm.bias.detach(), model.head[0].weight.detach(),
                                                  model.head[0].bias.detach(), model.head[1].weight.detach(), model.head[1].bias.detach()))
     torch.cuda.synchronize()
@@ -351,6 +373,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--op-dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--attn-variant", type=int, default=0)
+    ap.add_argument("--fuse-ln", action="store_true", help="fold the LayerNorms into the GEMM epilogues around them (A/B; default off)")
     ap.add_argument("--ref-clips", type=int, default=2, help="--impl reference: clips per step (bounded CPU sample)")
     ap.add_argument("--cpu-baseline-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -384,7 +407,7 @@ def main():
 
     S, grid_t = ARCH_T[args.arch]
     B = args.batch
-    model = get_maest(arch=args.arch, pretrained=False, op_dtype=args.op_dtype)
+    model = get_maest(arch=args.arch, pretrained=False, op_dtype=args.op_dtype, fuse_ln=args.fuse_ln)
     model.attn_variant = args.attn_variant
     model.load_state_dict(synth.synth_state_dict(grid_t, 400, seed=0), strict=False)   # random-init weights (no checkpoints offline)
     model = model.to(dev).eval()
@@ -478,7 +501,9 @@ def main():
     clips = B * world * args.steps
     value = clips / (ms_dev / 1e3)
     e2e_val = clips / (ms_e2e / 1e3)
-    per_step_launches = 5 + DEPTH * 7      # logmel, pos table, patch gather, patch GEMM, 12 x (LN, qkv, attn, proj, LN, fc1, fc2), pool/head
+    # logmel, pos table, patch gather, patch GEMM, 12 x (LN | LN-finalise, qkv, attn, proj, LN | LN-finalise, fc1, fc2), pool/head: the
+    # folded path replaces 23 LayerNorm kernels by 23 (tiny) statistics-finalise kernels, the launch count is the same
+    per_step_launches = 5 + DEPTH * 7
     line = dict(metric="clips/sec", value=value, unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
                 ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype=args.op_dtype + " operands, fp32 accumulate/residual/softmax/mel", data="synthetic",

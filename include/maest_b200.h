@@ -36,7 +36,7 @@ enum {
    *   LN(x) W^T + b  =  rstd * ((x*gamma) W^T)  -  rstd * mean * (W gamma)  +  (W beta + b)                                        */
   MAEST_EPI_STORE16_LN = 7, /* consumer (qkv): A = x*gamma op16; out16 = rstd*acc - rstd*mean*ln_vec[n] + bias[n]                   */
   MAEST_EPI_GELU16_LN = 8,  /* consumer (fc1): gelu_erf of the same                                                                 */
-  MAEST_EPI_RESID32_LN = 9  /* producer (proj, fc2): RESID32, plus out16b = x*ln_vec[n] (op16) and ln_stats[r] += (sum x, sum x^2) */
+  MAEST_EPI_RESID32_LN = 9  /* producer (proj, fc2): RESID32, plus out16b = x*ln_vec[n] (op16) and per-chunk row statistics      */
 };
 
 /* pooling modes (maest_pool_head_fwd) */
@@ -142,11 +142,14 @@ int32_t maest_ln_fold(const void* w16, const float* gamma, const float* beta, co
 
 /* Linear layers with the neighbouring LayerNorm folded in (epilogue = MAEST_EPI_*_LN).
  *   producer (RESID32_LN): out32 = resid + A W^T + bias;  out16b = out32 * ln_vec (gamma of the next LayerNorm);
- *                          ln_stats [M, 2] fp32 += (row sum, row sum of squares) -- the caller zeroes ln_stats first
- *   consumer (STORE16_LN / GELU16_LN): A = the producer's out16b; ln_vec = wg, bias = bf from maest_ln_fold; ln_eps = LN epsilon */
+ *                          ln_stats = partials fp32 [N/32, M, 4]: (pivot, sum (x - pivot), sum (x - pivot)^2, unused) of every
+ *                          32-column chunk of the new rows -- plain stores, no atomics, bit-reproducible
+ *   maest_ln_finalize:     partials -> stats fp32 [M, 2] = (rstd, -mean * rstd)
+ *   consumer (STORE16_LN / GELU16_LN): A = the producer's out16b; ln_stats = stats; ln_vec = wg, bias = bf from maest_ln_fold */
 int32_t maest_linear_ln_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, int32_t M, int32_t N,
                             int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out, const float* resid,
-                            float* ln_stats, const float* ln_vec, void* out16b, float ln_eps, void* stream);
+                            float* ln_stats, const float* ln_vec, void* out16b, void* stream);
+int32_t maest_ln_finalize(const float* partials, int32_t rows, int32_t n_features, float eps, float* stats, void* stream);
 
 /* Fused multi-head attention, d_head 64.  Replaces Attention.forward lines models/maest.py:362-375.
  * qkv op16 [B*N, 3*H*64] as written by the qkv linear (columns = [q|k|v][head][64]); out op16 [B*N, H*64].

@@ -45,7 +45,8 @@ SIGNATURES = {
                              c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p]),
     "maest_ln_fold": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "maest_linear_ln_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32,
-                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_float, c_void_p]),
+                                      c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "maest_ln_finalize": (c_int32, [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p]),
     "maest_set_gemm_mode": (c_int32, [c_int32]),
     "maest_attention_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "maest_attention_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -284,7 +284,7 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = addend; p.ld_out = int(ld_out);
   p.aux16 = aux16; p.k_splits = k_splits;
-  p.ln_stats = nullptr; p.ln_vec = nullptr; p.out16b = nullptr; p.ln_eps = 0.f; p.ln_inv_n = 0.f;
+  p.ln_stats = nullptr; p.ln_vec = nullptr; p.out16b = nullptr; p.ln_rows = 0;
   if (rows_per_group <= 0) { p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0; }
   else { p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; }
   if (epilogue == MAEST_EPI_RESID32 && !resid) return fail(-1, "gemm: RESID32 needs resid");
@@ -316,9 +316,18 @@ int32_t maest_ln_fold(const void* w16, const float* gamma, const float* beta, co
   return 0;
 }
 
+int32_t maest_ln_finalize(const float* partials, int32_t rows, int32_t n_features, float eps, float* stats, void* stream) {
+  if (rows <= 0) return 0;
+  if (n_features % 32) return fail(-1, "ln_finalize: n_features %% 32 must be 0");
+  ln_finalize_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(partials), rows, rows, n_features / 32, eps,
+                                                                             reinterpret_cast<float2*>(stats));
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
 int32_t maest_linear_ln_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, int32_t M, int32_t N,
                             int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out, const float* resid,
-                            float* ln_stats, const float* ln_vec, void* out16b, float ln_eps, void* stream) {
+                            float* ln_stats, const float* ln_vec, void* out16b, void* stream) {
   if (M <= 0 || N <= 0) return 0;
   if (epilogue != MAEST_EPI_STORE16_LN && epilogue != MAEST_EPI_GELU16_LN && epilogue != MAEST_EPI_RESID32_LN)
     return fail(-1, "linear_ln: epilogue %d is not a LayerNorm-folding epilogue", epilogue);
@@ -334,7 +343,7 @@ int32_t maest_linear_ln_fwd(const void* a, int64_t lda, const void* w, int64_t l
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = nullptr; p.ld_out = int(ld_out);
   p.aux16 = nullptr; p.k_splits = 1; p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0;
-  p.ln_stats = ln_stats; p.ln_vec = ln_vec; p.out16b = out16b; p.ln_eps = ln_eps; p.ln_inv_n = 1.0f / float(K);
+  p.ln_stats = ln_stats; p.ln_vec = ln_vec; p.out16b = out16b; p.ln_rows = M;
   cudaStream_t st = (cudaStream_t)stream;
   return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, false, false, ta, tb, p, st)
                                 : launch_gemm_dt<DT_F16>(epilogue, false, false, ta, tb, p, st);
@@ -438,7 +447,8 @@ int32_t maest_patch_tokens_fwd(const void* mel, int32_t mel_dtype, int32_t B, in
 
 size_t maest_encoder_workspace_bytes(int64_t rows) {
   // h16 [rows,768] | qkv16 [rows,2304] | o16 [rows,768] | u16 [rows,3072]  (+ 128 rows of slack per buffer) | LN stats [rows,2] fp32
-  return size_t(rows + 128) * (768 + 2304 + 768 + 3072) * 2 + size_t(rows + 128) * 8 + 1024;
+  // | LN stats [rows,2] fp32 | LN partials [24,rows,4] fp32
+  return size_t(rows + 128) * (768 + 2304 + 768 + 3072) * 2 + size_t(rows + 128) * (8 + 24 * 16) + 16 + 1024;
 }
 
 int32_t maest_encoder_fwd(float* x, int32_t B, int32_t N, const MaestBlockWeights* blocks, int32_t n_blocks,
@@ -454,19 +464,19 @@ int32_t maest_encoder_fwd(float* x, int32_t B, int32_t N, const MaestBlockWeight
   uint8_t* o16 = qkv16 + R * 2304 * 2;
   uint8_t* u16 = o16 + R * 768 * 2;
   float* stats = reinterpret_cast<float*>(u16 + R * 3072 * 2);
+  float* parts = stats + ((R * 2 + 3) & ~size_t(3));   // 16-byte aligned records
   int r;
   // LayerNorm folding (23 of the 24 LayerNorms disappear into the GEMM epilogues around them) needs the folded vectors of
   // every block; block 0's norm1 reads the token buffer written by K2 and stays a kernel.
   bool fold = true;
   for (int i = 0; i < n_blocks; ++i) fold = fold && blocks[i].qkv_wg && blocks[i].qkv_bf && blocks[i].fc1_wg && blocks[i].fc1_bf;
-  cudaStream_t st = (cudaStream_t)stream;
   bool h16_is_folded = false;   // h16 holds x * gamma of the next LayerNorm and `stats` its row sums
   for (int i = 0; i < n_blocks; ++i) {
     const MaestBlockWeights& w = blocks[i];
     const bool attn_only = last_attn_only && i == n_blocks - 1;
     if (h16_is_folded) {
       if ((r = maest_linear_ln_fwd(h16, 768, w.qkv_w, 768, w.qkv_bf, int(M), 2304, 768, op_dtype, MAEST_EPI_STORE16_LN, qkv16, 2304,
-                                   nullptr, stats, w.qkv_wg, nullptr, 1e-6f, stream))) return r;
+                                   nullptr, stats, w.qkv_wg, nullptr, stream))) return r;
     } else {
       if ((r = maest_layernorm_fwd(x, w.ln1_w, w.ln1_b, h16, op_dtype, int(M), 1e-6f, nullptr, nullptr, stream))) return r;
       if ((r = maest_linear_fwd(h16, 768, w.qkv_w, 768, w.qkv_b, int(M), 2304, 768, op_dtype, MAEST_EPI_STORE16, qkv16, 2304,
@@ -479,12 +489,12 @@ int32_t maest_encoder_fwd(float* x, int32_t B, int32_t N, const MaestBlockWeight
                               nullptr, 0, 0, 0, stream);
     }
     if (fold) {
-      // x += proj(o) and, in the same epilogue, h16 = x * gamma2 and stats = (sum x, sum x^2); fc1 finishes norm2
-      CUDA_OK(cudaMemsetAsync(stats, 0, size_t(M) * 8, st));
+      // x += proj(o) and, in the same epilogue, h16 = x * gamma2 and the row statistics of x; fc1 finishes norm2
       if ((r = maest_linear_ln_fwd(o16, 768, w.proj_w, 768, w.proj_b, int(M), 768, 768, op_dtype, MAEST_EPI_RESID32_LN, x, 768, x,
-                                   stats, w.ln2_w, h16, 0.f, stream))) return r;
+                                   parts, w.ln2_w, h16, stream))) return r;
+      if ((r = maest_ln_finalize(parts, int(M), 768, 1e-6f, stats, stream))) return r;
       if ((r = maest_linear_ln_fwd(h16, 768, w.fc1_w, 768, w.fc1_bf, int(M), 3072, 768, op_dtype, MAEST_EPI_GELU16_LN, u16, 3072,
-                                   nullptr, stats, w.fc1_wg, nullptr, 1e-6f, stream))) return r;
+                                   nullptr, stats, w.fc1_wg, nullptr, stream))) return r;
     } else {
       if ((r = maest_linear_fwd(o16, 768, w.proj_w, 768, w.proj_b, int(M), 768, 768, op_dtype, MAEST_EPI_RESID32, x, 768, x,
                                 nullptr, 0, 0, 0, stream))) return r;
@@ -494,9 +504,9 @@ int32_t maest_encoder_fwd(float* x, int32_t B, int32_t N, const MaestBlockWeight
     }
     if (fold && i + 1 < n_blocks) {
       // x += fc2(u) producing the operand and statistics of the NEXT block's norm1
-      CUDA_OK(cudaMemsetAsync(stats, 0, size_t(M) * 8, st));
       if ((r = maest_linear_ln_fwd(u16, 3072, w.fc2_w, 3072, w.fc2_b, int(M), 768, 3072, op_dtype, MAEST_EPI_RESID32_LN, x, 768, x,
-                                   stats, blocks[i + 1].ln1_w, h16, 0.f, stream))) return r;
+                                   parts, blocks[i + 1].ln1_w, h16, stream))) return r;
+      if ((r = maest_ln_finalize(parts, int(M), 768, 1e-6f, stats, stream))) return r;
       h16_is_folded = true;
     } else {
       if ((r = maest_linear_fwd(u16, 3072, w.fc2_w, 3072, w.fc2_b, int(M), 768, 3072, op_dtype, MAEST_EPI_RESID32, x, 768, x,

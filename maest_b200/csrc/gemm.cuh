@@ -39,7 +39,8 @@ enum : int {
   // finishes the normalisation per output element:  LN(x) W^T + b = rstd (xg W^T) - rstd mean (W gamma) + (W beta + b).
   EPI_STORE16_LN = 7,   // consumer: out16[r,n] = rstd_r * acc - rstd_r * mean_r * ln_vec[n] + bias[n]            (qkv)
   EPI_GELU16_LN = 8,    // consumer: out16[r,n] = gelu_erf(same)                                                   (fc1)
-  EPI_RESID32_LN = 9,   // producer: EPI_RESID32, plus out16b[r,n] = x * ln_vec[n] and ln_stats[r] += (sum x, sum x^2) (proj, fc2)
+  EPI_RESID32_LN = 9,   // producer: EPI_RESID32, plus out16b[r,n] = x * ln_vec[n] and, per row and 32-column chunk, the
+                        // partial statistics about a pivot                                                  (proj, fc2)
 };
 
 struct GemmParams {
@@ -53,10 +54,13 @@ struct GemmParams {
   int ld_out;
   int k_splits;          // >1: the K loop is split across CTAs (use with EPI_ATOMIC32)
   // LayerNorm folding (EPI_*_LN)
-  float* ln_stats;       // [rows][2] fp32: sum x, sum x^2 over the 768 features (producer: red.add; consumer: read)
+  float* ln_stats;       // producer: partials [N/32][ln_rows][4] = (pivot, sum (x - pivot), sum (x - pivot)^2, -) of every 32-column
+                         // chunk (plain stores, no atomics: results are bit-reproducible);  consumer: [rows][2] = (rstd, -mean * rstd)
+                         // as written by ln_finalize_kernel
+  long ln_rows;          // producer: row pitch of the partials array
   const float* ln_vec;   // consumer: W gamma [N];  producer: gamma of the LayerNorm that follows [N]
   void* out16b;          // producer: second output, x * gamma as op16, same shape / row stride as out
-  float ln_eps, ln_inv_n;  // consumer: epsilon and 1 / (features per row)
+
   // output row remap:  r = (m / rows_per_group) * group_stride + row_offset + (m % rows_per_group)
   int rows_per_group, group_stride, row_offset;
 };
@@ -176,10 +180,8 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
       ln_r[i] = 0.f; ln_mr[i] = 0.f;
       if (row_ok(i)) {
         const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * out_row(i));
-        const float mean = st.x * p.ln_inv_n;
-        const float var = fmaxf(fmaf(st.y, p.ln_inv_n, -mean * mean), 0.f);
-        ln_r[i] = rsqrtf(var + p.ln_eps);
-        ln_mr[i] = -mean * ln_r[i];
+        ln_r[i] = st.x;
+        ln_mr[i] = st.y;
       }
     }
   }
@@ -228,23 +230,25 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
     }
     if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) load_resid(cc + 1);   // next chunk's residual / table rows are in flight during the stores
     if constexpr (kLnProducer) {
-      // row statistics of the new residual stream: reduce the 4-column partials over the 8 lanes that share a row, one
-      // red.add pair per row and 32-column chunk.  All lanes take part in the shuffles (rows beyond M contribute zeros).
+      // row statistics of the new residual stream, per 32-column chunk, about a pivot (the chunk's first element, broadcast
+      // inside the 8 lanes that share a row) so that a large common offset of the row does not cancel: one broadcast + one
+      // 3-step butterfly carrying (sum d, sum d^2), d = x - pivot; ln_finalize_kernel merges the chunks.  All lanes take part
+      // in the shuffles (rows beyond M are not stored).  Partials are laid out [chunk][row] so the merge reads are coalesced.
+      const int chunk = n >> 5;
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 a = acc4[i];
-        const bool ok = row_ok(i);
-        float s1 = ok ? (a.x + a.y) + (a.z + a.w) : 0.f;
-        float s2 = ok ? fmaf(a.x, a.x, fmaf(a.y, a.y, fmaf(a.z, a.z, a.w * a.w))) : 0.f;
+        const float pv = __shfl_sync(0xffffffffu, a.x, lane & ~7);
+        const float dx = a.x - pv, dy = a.y - pv, dz = a.z - pv, dw = a.w - pv;
+        float s1 = (dx + dy) + (dz + dw);
+        float s2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
           s1 += __shfl_xor_sync(0xffffffffu, s1, o);
           s2 += __shfl_xor_sync(0xffffffffu, s2, o);
         }
-        if (ok && c4 == 0) {
-          atomicAdd(p.ln_stats + 2 * out_row(i), s1);
-          atomicAdd(p.ln_stats + 2 * out_row(i) + 1, s2);
-        }
+        if (row_ok(i) && c4 == 0)
+          *reinterpret_cast<float4*>(p.ln_stats + (long(chunk) * p.ln_rows + out_row(i)) * 4) = make_float4(pv, s1, s2, 0.f);
       }
     }
 #pragma unroll

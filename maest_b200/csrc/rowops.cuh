@@ -69,6 +69,29 @@ __global__ void __launch_bounds__(256) ln_fold_kernel(const void* __restrict__ w
   if (lane == 0) { wg[n] = a; bf[n] = (bias ? bias[n] : 0.f) + b; }
 }
 
+// LayerNorm folding, statistics side: merge the per-chunk partials (pivot, sum d, sum d^2 with d = x - pivot; 32 features per
+// chunk) written by the producer GEMM epilogue into (rstd, -mean * rstd) per row (pairwise update of Chan et al., fixed order).
+// Partials are [chunk][rows]: consecutive threads read consecutive 16-byte records.
+__global__ void __launch_bounds__(256) ln_finalize_kernel(const float4* __restrict__ part, int rows, long row_pitch, int nparts, float eps,
+                                                          float2* __restrict__ stats) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  if (row >= rows) return;
+  float mean = 0.f, m2 = 0.f, cnt = 0.f;
+#pragma unroll 8
+  for (int c = 0; c < nparts; ++c) {
+    const float4 q = __ldg(part + long(c) * row_pitch + row);
+    const float mc = q.x + q.y * (1.0f / 32.0f);               // chunk mean
+    const float m2c = fmaxf(q.z - q.y * q.y * (1.0f / 32.0f), 0.f);   // chunk sum of squared deviations from its mean
+    const float tot = cnt + 32.0f;
+    const float d = mc - mean;
+    mean += d * (32.0f / tot);
+    m2 += m2c + d * d * (cnt * 32.0f / tot);
+    cnt = tot;
+  }
+  const float rstd = rsqrtf(m2 / cnt + eps);
+  stats[row] = make_float2(rstd, -mean * rstd);
+}
+
 // emb[b, 0:768] = x[b,0], emb[b,768:1536] = x[b,1], emb[b,1536:2304] = mean(x[b,2:])   models/maest.py:825-829
 // grid (B, 768/64), 256 threads = 4 row-groups x 64 columns
 __global__ void __launch_bounds__(256) block_embedding_kernel(const float* __restrict__ x, int N, float* __restrict__ emb) {

@@ -205,7 +205,7 @@ class MAEST(nn.Module):
                  s_patchout_f_interleaved=0, s_patchout_t_indices=(), s_patchout_t_interleaved=0,
                  img_size=(96, 1875), patch_size=16, stride=(10, 10), in_chans=1, num_classes=400,
                  embed_dim=EMBED, depth=DEPTH, num_heads=HEADS, distilled=True, distilled_type="mean",
-                 op_dtype="fp16", attn_variant=0, fuse_ln=True):
+                 op_dtype="fp16", attn_variant=0, fuse_ln=False):
         super().__init__()
         if embed_dim != EMBED or num_heads != HEADS or patch_size != PATCH or in_chans != 1 or not distilled:
             raise NotImplementedError("the B200 path is specialised to ViT-Base/16, 12 heads, mono, distilled (all shipped MAEST configs)")
@@ -225,7 +225,10 @@ class MAEST(nn.Module):
         self.distilled_type = distilled_type
         self.op_dtype = op_dtype          # 16-bit GEMM operand type: "fp16" (default, tighter parity) or "bf16"
         self.attn_variant = attn_variant
-        self.fuse_ln = fuse_ln       # inference: fold norm1 / norm2 into the GEMM epilogues around them (23 of 24 LayerNorm launches)
+        # inference option: fold norm1 / norm2 into the GEMM epilogues around them (23 of 24 LayerNorm launches disappear).
+        # Off by default: measured on B200 at config 3 the heavier proj / fc2 / qkv epilogues cost what the LayerNorm kernels
+        # saved (1964 vs 1979 clips/s, profiles/README.md); results are bit-reproducible either way.
+        self.fuse_ln = fuse_ln
         if num_classes == 400:
             self.labels = discogs_400labels
         elif num_classes == 519:
@@ -528,7 +531,7 @@ def get_maest(arch, pretrained: bool = True, n_classes: int = 400, in_channels: 
               s_patchout_f: int = 0, s_patchout_f_indices: tuple = (), s_patchout_f_interleaved: int = 0,
               s_patchout_t_indices: tuple = (), s_patchout_t_interleaved: int = 0, distilled_type: str = "mean",
               checkpoint: str = None, checkpoint_swa_weigts: bool = True, checkpoint_discard_head: bool = False,
-              op_dtype: str = "fp16", fuse_ln: bool = True):
+              op_dtype: str = "fp16", fuse_ln: bool = False):
     """Same signature / defaults / arch table as the reference (`op_dtype` and `fuse_ln` are the only additions)."""
     if arch not in _ARCH_DEFAULT_T:
         raise NotImplementedError(f"model {arch} not implemented")        # models/maest.py:1530

@@ -163,8 +163,7 @@ def ln_fold(w16: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, bias: Op
 
 
 def linear_ln(a: torch.Tensor, w16: torch.Tensor, bias: torch.Tensor, epilogue: int, ln_stats: torch.Tensor, ln_vec: torch.Tensor,
-              out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, out16b: Optional[torch.Tensor] = None,
-              eps: float = 1e-6) -> torch.Tensor:
+              out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None, out16b: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Linear with the neighbouring LayerNorm folded in (include/maest_b200.h: maest_linear_ln_fwd)."""
     _need_cuda(a, w16, bias, ln_stats, ln_vec, out, resid, out16b)
     M, K = a.shape
@@ -175,8 +174,19 @@ def linear_ln(a: torch.Tensor, w16: torch.Tensor, bias: torch.Tensor, epilogue: 
         lib = _lib_for(a)
         _lib.check(lib.maest_linear_ln_fwd(a.data_ptr(), a.stride(0), w16.data_ptr(), w16.stride(0), _p(bias), M, N, K, _TORCH2DT[a.dtype],
                                            epilogue, out.data_ptr(), out.stride(0), _p(resid), ln_stats.data_ptr(), ln_vec.data_ptr(),
-                                           _p(out16b), float(eps), _stream()), "linear_ln")
+                                           _p(out16b), _stream()), "linear_ln")
     return out
+
+
+def ln_finalize(partials: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
+    """partials fp32 [n/32, M, 4] from a RESID32_LN producer -> stats fp32 [M, 2] = (rstd, -mean * rstd)."""
+    _need_cuda(partials)
+    nparts, M, _ = partials.shape
+    stats = torch.empty((M, 2), device=partials.device, dtype=torch.float32)
+    with torch.cuda.device(partials.device):
+        lib = _lib_for(partials)
+        _lib.check(lib.maest_ln_finalize(partials.data_ptr(), M, nparts * 32, float(eps), stats.data_ptr(), _stream()), "ln_finalize")
+    return stats
 
 
 def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 0, save_lse: bool = False):

@@ -12,6 +12,6 @@ for k in gemm_tn:14:4 attention_fwd:3:1 logmel:1:1 layernorm_to16:3:1; do
 done
 ncu --set full --clock-control none --import-source on -k regex:attention_bwd -s 2 -c 1 -o gpurun_out/prof_attention_bwd -f \
     python bench.py --mode train --batch 16 --steps 1 --warmup 3 > gpurun_out/ncu_attention_bwd.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1900 -c 700 --csv --log-file gpurun_out/launches_train.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1116 -c 372 --csv --log-file gpurun_out/launches_train.csv \
     python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/ncu_train.log 2>&1
 ls -la gpurun_out

@@ -95,8 +95,12 @@ def main():
     for src, dst in (("launches.csv", "launches_bench"), ("launches_train.csv", "launches_train_step")):
         lp = os.path.join(OUT, src)
         if os.path.exists(lp):
-            with open(os.path.join(PROF, f"{prefix}_{dst}.txt"), "w") as f:
-                summarize_launches(lp, f)
+            try:
+                with open(os.path.join(PROF, f"{prefix}_{dst}.txt"), "w") as f:
+                    summarize_launches(lp, f)
+            except StopIteration:      # the capture window held no kernels
+                os.remove(os.path.join(PROF, f"{prefix}_{dst}.txt"))
+                print(f"{src}: no launches captured")
     for name in sorted(os.listdir(OUT)):
         if name.endswith(".ncu-rep"):
             with open(os.path.join(PROF, f"{prefix}_{name[:-8]}_ncu_full.txt"), "w") as f:
