@@ -73,6 +73,14 @@ int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_str
  * data module).  Note: the reference extractor runs Essentia's framing, ours is the torchaudio framing of K1 (centre = True). */
 int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, void* stream);
 
+/* Validation metrics on the device.  Replaces sklearn's average_precision_score / roc_auc_score
+ * (average=None) as called by Module.on_test_validation_epoch_end, models/module.py:189-190, on host copies of the gathered
+ * predictions.  score_sorted / label_sorted: fp32 [n, C], every class column ordered by descending score (labels re-ordered
+ * with the same permutation).  ap, auc: fp64 [C]; n_pos: int32 [C] positives per class.  A class without positives or
+ * without negatives gets auc = NaN and ap = 0 / 1 (what scikit-learn >= 1.6 returns, with a warning). */
+int32_t maest_ap_roc_fwd(const float* score_sorted, const float* label_sorted, int32_t n, int32_t C, double* ap, double* auc,
+                         int32_t* n_pos, void* stream);
+
 /* Loader -> device ingest.  Replaces, per batch, DiscogsDataset.load_melspectrogram's
  * zero-pad + centring np.roll + transpose (discogs/dataset.py:120-139), DiscogsDataModule's norm_func
  * ((x - mean) / (2 std) in float16 arithmetic, discogs/datamodule.py:126-137) and roll_func (torch.roll along time, :111-123).

@@ -9,6 +9,7 @@
 #include "attention.cuh"
 #include "attention_bwd.cuh"
 #include "ingest.cuh"
+#include "metrics.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "logmel.cuh"
@@ -194,7 +195,7 @@ int init_dt() {
 extern "C" {
 
 const char* maest_last_error(void) { return g_err; }
-int32_t maest_abi_version(void) { return 4; }
+int32_t maest_abi_version(void) { return 5; }
 
 int32_t maest_init(int32_t device) {
   if (device < 0 || device >= 64) return fail(-1, "bad device %d", device);
@@ -246,6 +247,14 @@ int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_str
 int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, void* stream) {
   if (!raw_tm16) return fail(-1, "logmel_raw16: output is NULL");
   return logmel_launch(wav, B, S, wav_stride, nullptr, raw_tm16, stream);
+}
+
+int32_t maest_ap_roc_fwd(const float* score_sorted, const float* label_sorted, int32_t n, int32_t C, double* ap, double* auc,
+                         int32_t* n_pos, void* stream) {
+  if (n <= 0 || C <= 0) return 0;
+  ap_roc_kernel<<<(C + 127) / 128, 128, 0, (cudaStream_t)stream>>>(score_sorted, label_sorted, n, C, ap, auc, n_pos);
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int32_t maest_mel_ingest_fwd(const void* raw_tm16, const int32_t* frames_read, const int32_t* roll_shift, int32_t B, int32_t T,

@@ -49,7 +49,9 @@ def my_mixup(size, alpha):
 
 class Module(_LightningModule):
     """Drop-in for the reference's Lightning `Module` (models/module.py:44-276) for the hot path: `net`, `training_step`,
-    `forward`, `predict_step`, `configure_optimizers`.  Validation metrics / SWA plumbing stay Lightning's business."""
+    `forward`, `predict_step`, `configure_optimizers`, and the validation / test path (`validation_step`, `test_step`,
+    `on_validation_epoch_end`, `on_test_epoch_end`: twin-net evaluation with `net_swa` when the SWA callback created it, macro
+    AP / ROC AUC computed on the device instead of scikit-learn on host copies)."""
 
     @module_ing.capture
     def __init__(self, do_swa=True, swa_epoch_start=50, swa_lrs=2e-5, swa_freq=5, mixup_alpha=0.3, distributed_mode=False,
@@ -85,6 +87,70 @@ class Module(_LightningModule):
         x, f, y = batch
         logits, embed = self.forward(x, transformer_block=self.transformer_block)
         return {"logits": logits.detach().cpu(), "embeddings": embed.detach().cpu(), "filename": f}
+
+    # ---- validation / test (models/module.py:121-216) -----------------------------------------------------------------
+    @staticmethod
+    def _join(strings):
+        return "_".join(filter(lambda x: x, strings))
+
+    def _net_map(self):
+        net_map = [(None, self.net)]
+        if self.do_swa and hasattr(self, "net_swa"):       # helpers/swa_callback.py:43-44 creates net_swa on fit start
+            net_map.append(("swa", self.net_swa))
+        return net_map
+
+    def test_validation_step(self, batch, batch_idx, output_buffer, stage):
+        from . import ops
+        x, f, y = batch
+        outputs = {"y": y.detach()}
+        for name, net in self._net_map():
+            with torch.no_grad():
+                logits, _ = net(x)
+            loss, _ = ops.bce_logits(logits, y.to(logits.device))       # F.binary_cross_entropy_with_logits(...).mean()
+            outputs[self._join((name, "loss"))] = loss
+            outputs[self._join((name, "y_hat"))] = torch.sigmoid(logits.detach())
+            self.log(self._join((stage, "loss", name)), loss, batch_size=len(y), sync_dist=True)
+        output_buffer.append(outputs)
+        return outputs
+
+    def validation_step(self, batch, batch_idx):
+        return self.test_validation_step(batch, batch_idx, self.validation_outputs, "val")
+
+    def test_step(self, batch, batch_idx):
+        return self.test_validation_step(batch, batch_idx, self.test_outputs, "test")
+
+    def on_test_validation_epoch_end(self, outputs, stage):
+        """models/module.py:155-205 with the predictions kept on the GPU: per-class AP / ROC AUC by `ops.ap_roc` (sort +
+        threshold-scan kernel), macro-averaged.  Like scikit-learn (>= 1.6), a class with a single label value makes the macro
+        ROC AUC nan (with a warning)."""
+        from . import ops
+        result = {}
+        if not outputs:
+            return result
+        y = torch.cat([o["y"] for o in outputs], dim=0)
+        if self.distributed_mode:
+            y = self.all_gather(y).reshape(-1, y.shape[-1])
+        for name, _ in self._net_map():
+            loss = torch.stack([o[self._join((name, "loss"))] for o in outputs]).mean()
+            y_hat = torch.cat([o[self._join((name, "y_hat"))] for o in outputs], dim=0)
+            if self.distributed_mode:
+                loss = self.all_gather(loss).mean()
+                y_hat = self.all_gather(y_hat).reshape(-1, y_hat.shape[-1])
+            ap, auc, _ = ops.ap_roc(y.to(y_hat.device), y_hat)
+            if bool(torch.isnan(auc).any()):
+                import warnings
+                warnings.warn("Only one class is present in y_true for some label. ROC AUC score is not defined in that case.")
+            result.update({self._join((stage, "loss", name)): float(loss), self._join((stage, "ap", name)): float(ap.mean()),
+                           self._join((stage, "roc", name)): float(auc.mean())})
+        self.log_dict(result, sync_dist=True)
+        outputs.clear()
+        return result
+
+    def on_validation_epoch_end(self):
+        return self.on_test_validation_epoch_end(self.validation_outputs, "val")
+
+    def on_test_epoch_end(self):
+        return self.on_test_validation_epoch_end(self.test_outputs, "test")
 
     def set_prediction_tranformer_block(self, transformer_block):
         self.transformer_block = transformer_block

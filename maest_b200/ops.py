@@ -87,6 +87,24 @@ def logmel_raw16(wav: torch.Tensor) -> torch.Tensor:
     return out[0] if wav.dim() == 1 else out
 
 
+def ap_roc(y_true: torch.Tensor, y_score: torch.Tensor):
+    """Per-class (average precision, ROC AUC) of [n, C] CUDA tensors with scikit-learn's semantics (ties share a threshold).
+    The sort is torch's (library); the threshold scan runs in the ap_roc kernel.  Returns fp64 [C], fp64 [C], int32 [C] positives."""
+    _need_cuda(y_true, y_score)
+    assert y_true.shape == y_score.shape and y_score.dim() == 2
+    n, C = y_score.shape
+    s, idx = torch.sort(y_score.float(), dim=0, descending=True, stable=True)
+    lab = torch.gather(y_true.float(), 0, idx).contiguous()
+    s = s.contiguous()
+    ap = torch.empty(C, device=s.device, dtype=torch.float64)
+    auc = torch.empty(C, device=s.device, dtype=torch.float64)
+    npos = torch.empty(C, device=s.device, dtype=torch.int32)
+    with torch.cuda.device(s.device):
+        lib = _lib_for(s)
+        _lib.check(lib.maest_ap_roc_fwd(s.data_ptr(), lab.data_ptr(), n, C, ap.data_ptr(), auc.data_ptr(), npos.data_ptr(), _stream()), "ap_roc")
+    return ap, auc, npos
+
+
 def mel_ingest(raw: torch.Tensor, frames_read: Optional[torch.Tensor] = None, roll_shift: Optional[torch.Tensor] = None,
                norm_mean: Optional[float] = None, norm_std: Optional[float] = None) -> torch.Tensor:
     """raw fp16 CUDA [B, T, 96] (file windows, time-major) -> [B, 1, 96, T] fp16: zero-pad centring, normalisation and time
