@@ -232,7 +232,8 @@ def run_train(args):
     if world > 1:
         net.grad_allreduce = True          # per-block NCCL all-reduce of the flat gradient buffer, overlapped with backward
     mod = Module(net=net, mixup_alpha=0.3, do_swa=False).to(dev).train()
-    opt = torch.optim.AdamW(mod.parameters(), lr=2e-5, weight_decay=1e-4, fused=True)
+    from maest_b200.optim import FusedAdamW
+    opt = FusedAdamW(mod.parameters(), lr=2e-5, weight_decay=1e-4)      # one launch for all 152 parameter tensors
     torch.manual_seed(1 + rank)
     np.random.seed(1 + rank)
     g = torch.Generator(device=dev).manual_seed(7 + rank)

@@ -73,6 +73,16 @@ int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_str
  * data module).  Note: the reference extractor runs Essentia's framing, ours is the torchaudio framing of K1 (centre = True). */
 int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, void* stream);
 
+/* Fused AdamW (+ SWA running average) over all parameters in one launch.  Replaces
+ * torch.optim.AdamW as built by Module.get_optimizer (models/module.py:237-243) and the running average kept by the SWA
+ * callback (helpers/swa_callback.py:11-15 -> torch.optim.swa_utils avg_fn).
+ *   tensor_table: device array of { float* p; const float* g; float* m; float* v; float* swa (or NULL); int64 n; }
+ *   chunk_table:  device array of { int32 tensor; int32 pad; int64 start; }, one entry per 8192 elements of every tensor
+ *   step: 1-based step count (bias corrections);  grad_scale: multiplies the gradients first (1/loss_scale, or 1)
+ *   swa_inv: 1/(n_averaged+1) to also update the running average of every tensor with swa != NULL, or 0 */
+int32_t maest_adamw_step(const void* tensor_table, const void* chunk_table, int32_t n_chunks, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, int32_t step, float grad_scale, float swa_inv, void* stream);
+
 /* Validation metrics on the device.  Replaces sklearn's average_precision_score / roc_auc_score
  * (average=None) as called by Module.on_test_validation_epoch_end, models/module.py:189-190, on host copies of the gathered
  * predictions.  score_sorted / label_sorted: fp32 [n, C], every class column ordered by descending score (labels re-ordered

@@ -10,6 +10,7 @@
 #include "attention_bwd.cuh"
 #include "ingest.cuh"
 #include "metrics.cuh"
+#include "optim.cuh"
 #include "gemm.cuh"
 #include "gemm2.cuh"
 #include "logmel.cuh"
@@ -195,7 +196,7 @@ int init_dt() {
 extern "C" {
 
 const char* maest_last_error(void) { return g_err; }
-int32_t maest_abi_version(void) { return 5; }
+int32_t maest_abi_version(void) { return 6; }
 
 int32_t maest_init(int32_t device) {
   if (device < 0 || device >= 64) return fail(-1, "bad device %d", device);
@@ -247,6 +248,22 @@ int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_str
 int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, void* stream) {
   if (!raw_tm16) return fail(-1, "logmel_raw16: output is NULL");
   return logmel_launch(wav, B, S, wav_stride, nullptr, raw_tm16, stream);
+}
+
+int32_t maest_adamw_step(const void* tensor_table, const void* chunk_table, int32_t n_chunks, float lr, float beta1, float beta2,
+                         float eps, float weight_decay, int32_t step, float grad_scale, float swa_inv, void* stream) {
+  if (n_chunks <= 0) return 0;
+  if (step < 1) return fail(-1, "adamw: step counts from 1");
+  AdamWParams a;
+  a.tensors = reinterpret_cast<const OptTensor*>(tensor_table);
+  a.chunks = reinterpret_cast<const OptChunk*>(chunk_table);
+  a.lr = lr; a.beta1 = beta1; a.beta2 = beta2; a.eps = eps; a.weight_decay = weight_decay;
+  a.bias_c1 = float(1.0 - pow(double(beta1), double(step)));
+  a.bias_c2_sqrt = float(sqrt(1.0 - pow(double(beta2), double(step))));
+  a.grad_scale = grad_scale; a.swa_inv = swa_inv;
+  adamw_multi_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 0;
 }
 
 int32_t maest_ap_roc_fwd(const float* score_sorted, const float* label_sorted, int32_t n, int32_t C, double* ap, double* auc,

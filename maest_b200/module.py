@@ -155,10 +155,32 @@ class Module(_LightningModule):
     def set_prediction_tranformer_block(self, transformer_block):
         self.transformer_block = transformer_block
 
-    def configure_optimizers(self):
-        # models/module.py:237-243: AdamW over all parameters
+    def get_optimizer(self, params):
+        """models/module.py:236-243.  On CUDA parameters the AdamW step is one fused launch (maest_b200.optim.FusedAdamW, same
+        arithmetic); `fused_optimizer=False` in the optimizer config keeps torch.optim.AdamW."""
         cfg = self.optimizer_cfg
-        return torch.optim.AdamW(self.parameters(), lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+        params = list(params)
+        if not cfg["adamw"]:
+            return torch.optim.Adam(params, lr=cfg["lr"])
+        if cfg.get("fused_optimizer", True) and params and params[0].is_cuda:
+            from .optim import FusedAdamW
+            return FusedAdamW(params, lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+        return torch.optim.AdamW(params, lr=cfg["lr"], weight_decay=cfg["weight_decay"])
+
+    def get_scheduler_lambda(self):
+        from .optim import get_scheduler_lambda
+        c = self.optimizer_cfg
+        return get_scheduler_lambda(c["warm_up_len"], c["ramp_down_start"], c["ramp_down_len"], c["last_lr_value"], c["schedule_mode"])
+
+    def get_lr_scheduler(self, optimizer):
+        if self.optimizer_cfg["schedule_mode"] in {"exp_lin", "cos_cyc"}:       # models/module.py:225-231
+            return torch.optim.lr_scheduler.LambdaLR(optimizer, self.get_scheduler_lambda())
+        raise RuntimeError(f"schedule_mode={self.optimizer_cfg['schedule_mode']} Unknown.")
+
+    def configure_optimizers(self):
+        # models/module.py:245-254: {"optimizer": AdamW over all parameters, "lr_scheduler": LambdaLR(epoch lambda)}
+        optimizer = self.get_optimizer(self.parameters())
+        return {"optimizer": optimizer, "lr_scheduler": self.get_lr_scheduler(optimizer)}
 
 
 def allreduce_gradients(module: torch.nn.Module, group=None) -> int:

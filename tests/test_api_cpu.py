@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.maest_abi_version() == 5
+    assert lib.maest_abi_version() == 6
     assert lib.maest_encoder_workspace_bytes(1000) > 1000 * 13824
     assert lib.maest_patch_workspace_bytes(2, 558) >= 2 * 558 * 512 + 558 * 3072
 

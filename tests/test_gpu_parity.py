@@ -45,7 +45,7 @@ def m30():
 
 def test_native_library_is_loaded():
     lib = _lib.init(0)
-    assert lib.maest_abi_version() == 5
+    assert lib.maest_abi_version() == 6
     maps = open("/proc/self/maps").read()
     assert "libmaest_b200.so" in maps
 
