@@ -285,7 +285,7 @@ def run_train(args):
                     config=dict(workload=f"maest_30s_from_passt_pretrain training step: mel [{B},1,96,1875] fp16 per GPU, s_patchout_t=90 -> {N} tokens, "
                                          "mixup 0.3, BCE, fwd+bwd" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + AdamW step",
                                 batch_per_gpu=B, tokens=N, gflop_per_clip_fwd=fl["total"] / 1e9),
-                    loss=float(loss), grad_elements_allreduced=n_grad[0], clocks=clocks,
+                    loss=float(loss.detach()), grad_elements_allreduced=n_grad[0], clocks=clocks,
                     model_tflops=tf, model_frac_of_bf16_sustained=tf / peaks["bf16_tflops_sustained"],
                     gpu_launches=args.steps * (12 * 30 + 12))
         print(json.dumps(line), flush=True)
@@ -523,7 +523,7 @@ def main():
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         total_ms = sum(v["ms_per_step"] for v in breakdown.values())
         traffic = None
-        tpath = os.path.join(ROOT, "profiles", "r01_gemm_traffic.json")
+        tpath = next((q for q in (os.path.join(ROOT, "profiles", n) for n in ("r01b_gemm_traffic.json", "r01_gemm_traffic.json")) if os.path.exists(q)), "")
         if os.path.exists(tpath) and B == 64 and args.arch == "discogs-maest-30s-pw-129e":
             with open(tpath) as tf:
                 traffic = json.load(tf)["gemm_family_bytes_per_step"] / gemm_launches    # measured DRAM bytes per launch (ncu --set full)

@@ -42,7 +42,7 @@ def test_training_step_vs_reference(golden, dt, tol):
     mix = my_mixup(2, 0.3)                      # same host RNG order as the reference
     loss, logits = training_forward(m, x.cuda(), y.cuda(), mix)
     assert logits.shape == (2, 400) and not logits.requires_grad
-    assert abs(float(loss) - float(g["loss"])) < 1e-4
+    assert abs(float(loss.detach()) - float(g["loss"])) < 1e-4
     loss.backward()
     grads = {n: p.grad for n, p in m.named_parameters()}
     assert grads["head_dist.weight"] is None and grads["head_dist.bias"] is None     # unused in "mean" mode, as in the reference
