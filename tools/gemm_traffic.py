@@ -39,7 +39,7 @@ def main(prefix):
     tot = 12 * sum(v["dram_read_bytes"] + v["dram_write_bytes"] for v in per.values())
     out = dict(source=f"ncu --set full --clock-control none, profiles/{prefix}_prof_gemm_ncu_full.txt (config 3, B=64, fp16 operands)",
                per_launch=per, gemm_family_bytes_per_step=tot, launches_per_step=48)
-    with open(os.path.join(ROOT, "profiles", f"{prefix}_gemm_traffic.json"), "w") as f:
+    with open(os.path.join(os.environ.get("NCU_SUMMARY_DIR") or os.path.join(ROOT, "profiles"), f"{prefix}_gemm_traffic.json"), "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps({k: (round(v["duration_us"], 1), round((v["dram_read_bytes"] + v["dram_write_bytes"]) / 1e6)) for k, v in per.items()}), tot)
 

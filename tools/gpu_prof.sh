@@ -16,4 +16,10 @@ ncu --set full --clock-control none --import-source on -k regex:attention_bwd -s
     python bench.py --mode train --batch 16 --steps 1 --warmup 3 > gpurun_out/ncu_attention_bwd.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 1116 -c 372 --csv --log-file gpurun_out/launches_train.csv \
     python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/ncu_train.log 2>&1
-ls -la gpurun_out
+# the .ncu-rep files are too large to travel back (64 MiB cap): summarise them here, keep only the text
+export NCU_SUMMARY_DIR=gpurun_out/profiles_out
+mkdir -p $NCU_SUMMARY_DIR
+python tools/ncu_summarize.py ${PREFIX:-r01c} > gpurun_out/summarize.log 2>&1
+python tools/gemm_traffic.py ${PREFIX:-r01c} >> gpurun_out/summarize.log 2>&1
+rm -f gpurun_out/*.ncu-rep
+ls -la gpurun_out gpurun_out/profiles_out
