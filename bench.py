@@ -523,7 +523,9 @@ def main():
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         total_ms = sum(v["ms_per_step"] for v in breakdown.values())
         traffic = None
-        tpath = next((q for q in (os.path.join(ROOT, "profiles", n) for n in ("r01b_gemm_traffic.json", "r01_gemm_traffic.json")) if os.path.exists(q)), "")
+        import glob
+        tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))      # newest round's ncu capture
+        tpath = tfiles[-1] if tfiles else ""
         if os.path.exists(tpath) and B == 64 and args.arch == "discogs-maest-30s-pw-129e":
             with open(tpath) as tf:
                 traffic = json.load(tf)["gemm_family_bytes_per_step"] / gemm_launches    # measured DRAM bytes per launch (ncu --set full)
