@@ -286,7 +286,7 @@ int32_t maest_mel_ingest_fwd(const void* raw_tm16, const int32_t* frames_read, c
   p.norm_2std = __float2half_rn(norm_std * 2.0f);
   p.out = reinterpret_cast<__half*>(out);
   dim3 grid((T + ING_FRAMES - 1) / ING_FRAMES, B);
-  mel_ingest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(p);
+  mel_ingest_kernel<<<grid, ING_THREADS, 0, (cudaStream_t)stream>>>(p);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

@@ -22,10 +22,11 @@ struct IngestParams {
   __half* out;              // [B, 96, T]
 };
 
-constexpr int ING_FRAMES = 64;   // output frames per CTA
+constexpr int ING_FRAMES = 64;    // output frames per CTA
+constexpr int ING_THREADS = 192;  // load phase: 48 band pairs x 4 frames per pass; store phase: 32 frame pairs x 6 bands per pass
 
-__global__ void __launch_bounds__(256) mel_ingest_kernel(const IngestParams p) {
-  __shared__ __half tile[ING_FRAMES][98];   // [frame][band], padded
+__global__ void __launch_bounds__(ING_THREADS) mel_ingest_kernel(const IngestParams p) {
+  __shared__ __align__(4) __half tile[96][ING_FRAMES + 2];   // [band][frame]: rows of 33 words, conflict-free in both phases
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * ING_FRAMES;
   const int nfr = min(ING_FRAMES, p.T - t0);
@@ -35,22 +36,38 @@ __global__ void __launch_bounds__(256) mel_ingest_kernel(const IngestParams p) {
   if (sf < 0) sf += p.T;
   const __half2* raw2 = reinterpret_cast<const __half2*>(p.raw + long(b) * p.T * 96);
   const __half2 mean2 = __half2half2(p.norm_mean), std2 = __half2half2(p.norm_2std);
-  for (int i = threadIdx.x; i < nfr * 48; i += 256) {
-    const int f = i / 48, bp = i - f * 48;
-    int src = t0 + f - sf;                  // undo the time roll
+  {   // load: consecutive threads -> consecutive band pairs of one frame (192-byte rows of the file window)
+    const int bp = threadIdx.x % 48, f0 = threadIdx.x / 48;
+    int src = t0 + f0 - sf;                 // undo the time roll ...
     if (src < 0) src += p.T;
-    src -= pad_half;                        // undo the centring roll of the zero padding
+    src -= pad_half;                        // ... and the centring roll of the zero padding
     if (src < 0) src += p.T;
-    __half2 v = src < n ? raw2[long(src) * 48 + bp] : __half2half2(__ushort_as_half(0));
-    if (p.do_norm) v = __h2div(__hsub2(v, mean2), std2);
-    tile[f][2 * bp] = __low2half(v);
-    tile[f][2 * bp + 1] = __high2half(v);
+    for (int f = f0; f < nfr; f += 4) {
+      __half2 v = src < n ? __ldg(raw2 + long(src) * 48 + bp) : __half2half2(__ushort_as_half(0));
+      if (p.do_norm) v = __h2div(__hsub2(v, mean2), std2);
+      tile[2 * bp][f] = __low2half(v);
+      tile[2 * bp + 1][f] = __high2half(v);
+      src += 4;
+      if (src >= p.T) src -= p.T;
+    }
   }
   __syncthreads();
-  __half* out = p.out + long(b) * 96 * p.T + t0;
-  for (int i = threadIdx.x; i < 96 * ING_FRAMES; i += 256) {
-    const int band = i / ING_FRAMES, f = i - band * ING_FRAMES;
-    if (f < nfr) out[long(band) * p.T + f] = tile[f][band];
+  {   // store: consecutive threads -> consecutive frame PAIRS of one band; 4-byte stores wherever the row allows it (rows
+      // of T fp16 start on odd element offsets for every other band when T is odd)
+    const int k = threadIdx.x % 32, band0 = threadIdx.x / 32;
+    for (int band = band0; band < 96; band += 6) {
+      const long row = (long(b) * 96 + band) * p.T + t0;
+      __half* out = p.out + row;
+      const int mis = int(row & 1);          // 1: element 0 of this tile row is not 4-byte aligned
+      const int f = 2 * k + mis;             // this thread's pair covers frames f, f + 1
+      if (f + 1 < nfr) {
+        const __half2 v = __halves2half2(tile[band][f], tile[band][f + 1]);
+        *reinterpret_cast<__half2*>(out + f) = v;
+      } else if (f < nfr) {
+        out[f] = tile[band][f];
+      }
+      if (mis && k == 0 && nfr > 0) out[0] = tile[band][0];
+    }
   }
 }
 
