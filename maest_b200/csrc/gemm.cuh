@@ -108,6 +108,17 @@ __device__ __forceinline__ float gelu_erf_grad_fast(float x) {
   return fmaf(0.5f, erf_v, 0.5f) + x * e * 0.3989422804014327f;
 }
 
+// The staging tile is addressed in the shared window explicitly: through the generic pointer ptxas emitted generic LD.E / ST.E
+// (address-space resolution on every access) for what are plain ld.shared / st.shared.
+__device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
+  float4 r;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "r"(saddr) : "memory");
+  return r;
+}
+
 // Drain one accumulator half-tile (32 TMEM lanes x up to 128 columns) of the calling epilogue warp: TMEM -> registers ->
 // swizzled per-warp smem tile -> row-coalesced fused epilogue.  m0 / n0: first output row / column of this warp's
 // sub-tile; `release_tmem()` is invoked once, as soon as the last accumulator column has been read.
@@ -186,6 +197,10 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
     }
   }
   load_resid(0);
+  const uint32_t stg_s = smem_u32(stg);
+  // bias of the next chunk is fetched while the current one is processed (its L2 / L1 latency sat on the first FADD of every chunk)
+  float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.bias != nullptr && nchunks > 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c4 * 4));
   mbar_wait(tfull, aphase);
   tc_fence_after();
   if (nchunks == 0) {
@@ -204,26 +219,23 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
     }
     __syncwarp();              // previous chunk's staging reads are complete
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      *reinterpret_cast<uint4*>(stg + lane * 128 + ((j ^ (lane & 7)) << 4)) =
-          make_uint4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-    }
+    for (int j = 0; j < 8; ++j) sts_v4(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
     __syncwarp();
     const int col = n + c4 * 4;
-    float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (p.bias != nullptr) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col));
+    const float4 b4_cur = b4;
+    if (p.bias != nullptr && cc + 1 < nchunks) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32));
     float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
     if constexpr (kLnConsumer || kLnProducer) g4 = __ldg(reinterpret_cast<const float4*>(p.ln_vec + col));
     float4 acc4[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rl = i * 4 + sub_row;
-      float4 a = *reinterpret_cast<const float4*>(stg + rl * 128 + ((c4 ^ (rl & 7)) << 4));
+      float4 a = lds_f4(stg_s + rl * 128 + ((c4 ^ (rl & 7)) << 4));
       if constexpr (kLnConsumer) {   // finish the LayerNorm: rstd * acc - rstd * mean * (W gamma) + (W beta + b)
-        a.x = fmaf(a.x, ln_r[i], fmaf(ln_mr[i], g4.x, b4.x)); a.y = fmaf(a.y, ln_r[i], fmaf(ln_mr[i], g4.y, b4.y));
-        a.z = fmaf(a.z, ln_r[i], fmaf(ln_mr[i], g4.z, b4.z)); a.w = fmaf(a.w, ln_r[i], fmaf(ln_mr[i], g4.w, b4.w));
+        a.x = fmaf(a.x, ln_r[i], fmaf(ln_mr[i], g4.x, b4_cur.x)); a.y = fmaf(a.y, ln_r[i], fmaf(ln_mr[i], g4.y, b4_cur.y));
+        a.z = fmaf(a.z, ln_r[i], fmaf(ln_mr[i], g4.z, b4_cur.z)); a.w = fmaf(a.w, ln_r[i], fmaf(ln_mr[i], g4.w, b4_cur.w));
       } else {
-        a.x += b4.x; a.y += b4.y; a.z += b4.z; a.w += b4.w;
+        a.x += b4_cur.x; a.y += b4_cur.y; a.z += b4_cur.z; a.w += b4_cur.w;
       }
       if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
       acc4[i] = a;
@@ -254,6 +266,18 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 a = acc4[i];
+      if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_LN) {
+        // no global read depends on the row here: do the math for every lane and predicate only the store (the per-row
+        // branch around the GELU cost a BSSY / BRA / BSYNC triple per row and chunk)
+        a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
+        if (row_ok(i)) {
+          uint2 o;
+          o.x = O::pack(a.x, a.y);
+          o.y = O::pack(a.z, a.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.out) + out_row(i) * p.ld_out + col) = o;
+        }
+        continue;
+      }
       if (!row_ok(i)) continue;
       const long r = out_row(i);
       if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELUBWD16 || kLnConsumer) {
