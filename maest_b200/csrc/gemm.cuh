@@ -205,7 +205,8 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
   tc_fence_after();
   if (nchunks == 0) {
     tc_fence_before();
-    release_tmem();
+    __syncwarp();
+    if (lane == 0) release_tmem();     // one arrival per warp (the barrier counts warps, not threads)
   }
 #pragma unroll 1
   for (int cc = 0; cc < nchunks; ++cc) {
@@ -215,7 +216,8 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
     tc_wait_ld();
     if (cc == nchunks - 1) {   // accumulator fully drained by this warp: hand the TMEM stage back early
       tc_fence_before();
-      release_tmem();
+      __syncwarp();
+      if (lane == 0) release_tmem();   // one arrival per warp: 8 (16 for a CTA pair, half of them remote) instead of 256 (512)
     }
     __syncwarp();              // previous chunk's staging reads are complete
 #pragma unroll
@@ -359,7 +361,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], GEMM_EPI_WARPS * 32);
+      mbar_init(&tempty_bar[i], GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }

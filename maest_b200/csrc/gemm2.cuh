@@ -25,7 +25,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
   uint64_t* full_bar = bars;                            // [STAGES]  (only the leader's copies are waited on)
   uint64_t* empty_bar = bars + GEMM2_STAGES;            // [STAGES]  (each CTA waits on its own; signalled by multicast commit)
   uint64_t* tfull_bar = bars + 2 * GEMM2_STAGES;        // [2]       (multicast commit)
-  uint64_t* tempty_bar = bars + 2 * GEMM2_STAGES + 2;   // [2]       (leader's copy: 2 x 256 arrivals)
+  uint64_t* tempty_bar = bars + 2 * GEMM2_STAGES + 2;   // [2]       (leader's copy: one arrival per epilogue warp of both CTAs)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * GEMM2_STAGES + 4);
 
   const int warp = threadIdx.x >> 5;
@@ -50,7 +50,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS * 32);
+      mbar_init(&tempty_bar[i], 2 * GEMM_EPI_WARPS);
     }
     fence_mbar_init();
   }
