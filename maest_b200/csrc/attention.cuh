@@ -401,7 +401,8 @@ __device__ __forceinline__ void att_spec_tile(const int j, const int valid, cons
   for (int c = 0; c < NC / 32; ++c) tmem_ld32(tS + lane_off + uint32_t(c * 32), *reinterpret_cast<uint32_t(*)[32]>(s + 32 * c));
   tc_wait_ld();
   tc_fence_before();
-  mbar_arrive(s_free);          // S_j is in registers: the tensor pipe may overwrite it with S_{j+1}
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(s_free);   // S_j is in registers (one arrival per warp): the tensor pipe may overwrite it with S_{j+1}
   ATT_CLK(1);
   if (valid < NC) {
 #pragma unroll
@@ -489,7 +490,8 @@ __device__ __forceinline__ void att_spec_tile(const int j, const int valid, cons
   ATT_CLK(3);
   tc_wait_st();
   tc_fence_before();
-  mbar_arrive(p_full);
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(p_full);   // one arrival per warp: 4 instead of 128 serialised mbarrier updates per tile
   ATT_CLK(6);
 }
 
@@ -555,8 +557,8 @@ attention_fwd_spec_kernel(const __grid_constant__ CUtensorMap tmap_q, const __gr
   if (warp == 5) {
     if (lane == 0) {
       mbar_init(s_full, 1);
-      mbar_init(s_free, 128);
-      mbar_init(p_full, 128);
+      mbar_init(s_free, 4);
+      mbar_init(p_full, 4);
       mbar_init(o_done, 1);
       fence_mbar_init();
     }

@@ -49,7 +49,7 @@ if __name__ == "__main__":
         sys.exit(0)
     libs = [None] + (sorted(glob.glob(os.path.join(ROOT, "maest_b200", "lib", "libmaest_b200_x*.so"))) if os.environ.get("ATT_XLIBS") else [])
     for lib in libs:
-        for variant in [0, 2, 16]:
+        for variant in [0, 2]:
             env = dict(os.environ, ATT_CHILD="1", ATT_VARIANT=str(variant))
             if lib:
                 env["MAEST_B200_LIB"] = lib
