@@ -53,6 +53,13 @@ class MelWindowBatcher:
         assert len(files) <= self.B
         buf = self.host.numpy()
         for i, f in enumerate(files):
+            if str(f).endswith(".npy"):
+                # discogs/dataset.py:72-87: whole-array files; no offset draw, the first T frames (or all of them, padded)
+                arr = np.load(f).astype("float16")
+                n = min(arr.shape[0], self.T)
+                buf[i, :n] = arr[:n]
+                self.host_n[i] = n
+                continue
             frames_num = os.stat(f).st_size // (2 * N_BANDS)
             off, n = window_of(frames_num, self.T, None if offsets is None else offsets[i])
             fp = np.memmap(f, dtype="float16", mode="r", shape=(n, N_BANDS), offset=off * N_BANDS * 2)

@@ -22,6 +22,19 @@ def load_window(raw: np.ndarray, melspectrogram_size: int, offset: int) -> np.nd
     return np.expand_dims(mel.T, 0)                                         # :137-138
 
 
+def load_npy(arr: np.ndarray, melspectrogram_size: int) -> np.ndarray:
+    """The `.npy` branch of load_melspectrogram (discogs/dataset.py:72-87): no window offset; short arrays are zero-padded
+    and the padding centred, long ones truncated to the first `melspectrogram_size` frames."""
+    mel = arr.astype("float16")
+    if mel.shape[0] < melspectrogram_size:
+        padding_size = melspectrogram_size - mel.shape[0]
+        mel = np.vstack([mel, np.zeros([padding_size, mel.shape[1]], dtype="float16")])
+        mel = np.roll(mel, padding_size // 2, axis=0)
+    else:
+        mel = mel[:melspectrogram_size, :]
+    return np.expand_dims(mel.T, 0)
+
+
 def norm(x: np.ndarray, norm_mean: float, norm_std: float) -> np.ndarray:
     """discogs/datamodule.py:130-134 on a float16 array: numpy keeps float16 (the Python floats are weak scalars)."""
     return (x - norm_mean) / (norm_std * 2)
