@@ -87,13 +87,19 @@ int make_tmap_f32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols,
 
 int g_gemm_pair_mode = 2;   // 0: 1-CTA tiles, 1: CTA-pair (cta_group::2) tiles, 2: per-shape choice (default)
 
-// Measured on B200 (M = 107 840): the pair kernel wins where the mainloop dominates (qkv 0.322 -> 0.312 ms, fc2 0.434 -> 0.400 ms)
-// and loses where the epilogue does (proj 0.188 -> 0.197 ms, fc1+GELU 0.524 -> 0.543 ms).
-inline bool use_pair_kernel(int epi, int K) {
-  if (epi == MAEST_EPI_GELU16_LN) return false;   // not instantiated for the pair kernel (the epilogue-bound shape)
+// Measured on B200 (M = 107 840): the pair kernel wins where the mainloop dominates (qkv 0.329 -> 0.289 ms, fc2 0.434 -> 0.400 ms)
+// and, with the packed / TMA-store epilogue, for the inference fc1 + GELU (0.476 -> 0.450 ms); it loses for proj (0.188 -> 0.197 ms)
+// and is not used for the training forward's two-output GELU epilogue.
+inline bool use_pair_kernel(int epi, int K, bool has_aux = false) {
+  if (epi == MAEST_EPI_GELU16_LN) return false;   // not instantiated for the pair kernel
   if (g_gemm_pair_mode != 2) return g_gemm_pair_mode == 1;
-  return epi == MAEST_EPI_STORE16 || epi == MAEST_EPI_STORE16_LN || ((epi == MAEST_EPI_RESID32 || epi == MAEST_EPI_RESID32_LN) && K >= 2048);
+  return epi == MAEST_EPI_STORE16 || epi == MAEST_EPI_STORE16_LN || (epi == MAEST_EPI_GELU16 && !has_aux) ||
+         ((epi == MAEST_EPI_RESID32 || epi == MAEST_EPI_RESID32_LN) && K >= 2048);
 }
+
+// Tensor map of the 16-bit output for the TMA-store epilogues (STORE16 / GELU16 and their LN-folded forms); set by the entry
+// points right before the dispatch, ignored by every other epilogue.
+static thread_local CUtensorMap t_tmap_c;
 
 template <int DT, int EPI>
 int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
@@ -101,7 +107,7 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams&
   const int sms = g_num_sms[cur_device()];
   int pairs = sms / 2;
   if (pairs > num_tiles) pairs = num_tiles;
-  gemm2_tn_kernel<DT, EPI><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, p);
+  gemm2_tn_kernel<DT, EPI><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, t_tmap_c, p);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -112,7 +118,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   const int num_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + GEMM_BN - 1) / GEMM_BN) * splits;
   const int sms = g_num_sms[cur_device()];
   const int grid = num_tiles < sms ? num_tiles : sms;
-  gemm_tn_kernel<DT, EPI, A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, p);
+  gemm_tn_kernel<DT, EPI, A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, t_tmap_c, p);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -120,7 +126,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
 // the instantiated (epilogue, operand-major) combinations: forward (K,K), dgrad (K,MN), wgrad (MN,MN)
 template <int DT>
 int launch_gemm_dt(int epi, bool a_mn, bool b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
-  if (!a_mn && !b_mn && p.k_splits <= 1 && use_pair_kernel(epi, p.K)) {
+  if (!a_mn && !b_mn && p.k_splits <= 1 && use_pair_kernel(epi, p.K, p.aux16 != nullptr)) {
     switch (epi) {
       case MAEST_EPI_STORE16: return launch_gemm2<DT, EPI_STORE16>(ta, tb, p, st);
       case MAEST_EPI_GELU16:
@@ -305,7 +311,7 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   int r;
   // K-major operand: matrix [rows = M|N, cols = K]; MN-major operand: matrix [rows = K, cols = M|N]
   if ((r = a_mn ? make_tmap(&ta, a, op_dtype, K, M, lda, 64) : make_tmap(&ta, a, op_dtype, M, K, lda, GEMM_BM))) return r;
-  const bool pair_kernel = !a_mn && !b_mn && k_splits <= 1 && use_pair_kernel(epilogue, K);   // each CTA of a pair loads half of the W tile
+  const bool pair_kernel = !a_mn && !b_mn && k_splits <= 1 && use_pair_kernel(epilogue, K, aux16 != nullptr);   // each CTA of a pair loads half of the W tile
   if ((r = b_mn ? make_tmap(&tb, b, op_dtype, K, N, ldb, 64) : make_tmap(&tb, b, op_dtype, N, K, ldb, pair_kernel ? 128 : GEMM_BN))) return r;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = addend; p.ld_out = int(ld_out);
@@ -315,7 +321,10 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   else { p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; }
   if (epilogue == MAEST_EPI_RESID32 && !resid) return fail(-1, "gemm: RESID32 needs resid");
   if (epilogue == MAEST_EPI_RESID32 && rows_per_group > 0) return fail(-1, "gemm: RESID32 does not support row remapping");
+  if ((epilogue == MAEST_EPI_STORE16 || epilogue == MAEST_EPI_GELU16) && rows_per_group > 0) return fail(-1, "gemm: the 16-bit epilogues do not support row remapping");
   if (epilogue == MAEST_EPI_GELUBWD16 && !aux16) return fail(-1, "gemm: GELUBWD16 needs the saved pre-activation (aux16)");
+  if ((epilogue == MAEST_EPI_STORE16 || (epilogue == MAEST_EPI_GELU16 && !aux16)) &&
+      (r = make_tmap(&t_tmap_c, out, op_dtype, M, N, ld_out, 32))) return r;     // TMA-store epilogue: [32 rows x 64 columns] boxes
   cudaStream_t st = (cudaStream_t)stream;
   return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st)
                                 : launch_gemm_dt<DT_F16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st);
@@ -370,6 +379,7 @@ int32_t maest_linear_ln_fwd(const void* a, int64_t lda, const void* w, int64_t l
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = nullptr; p.ld_out = int(ld_out);
   p.aux16 = nullptr; p.k_splits = 1; p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0;
   p.ln_stats = ln_stats; p.ln_vec = ln_vec; p.out16b = out16b; p.ln_rows = M;
+  if ((epilogue == MAEST_EPI_STORE16_LN || epilogue == MAEST_EPI_GELU16_LN) && (r = make_tmap(&t_tmap_c, out, op_dtype, M, N, ld_out, 32))) return r;
   cudaStream_t st = (cudaStream_t)stream;
   return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, false, false, ta, tb, p, st)
                                 : launch_gemm_dt<DT_F16>(epilogue, false, false, ta, tb, p, st);

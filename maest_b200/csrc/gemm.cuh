@@ -123,7 +123,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
 // swizzled per-warp smem tile -> row-coalesced fused epilogue.  m0 / n0: first output row / column of this warp's
 // sub-tile; `release_tmem()` is invoked once, as soon as the last accumulator column has been read.
 template <int DT, int EPI, typename ReleaseFn>
-__device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8_t* stg, uint32_t taddr, int m0, int n0, int lane,
+__device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const CUtensorMap* tmap_c, uint8_t* stg, uint32_t taddr, int m0, int n0, int lane,
                                                       uint64_t* tfull, uint32_t aphase, ReleaseFn release_tmem) {
   using O = Op16<DT == DT_BF16 ? DT_BF16 : DT_F16>;
   const bool identity_rows = p.rows_per_group == 0x7fffffff;   // set by the host when no remap is requested
@@ -196,6 +196,19 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
       }
     }
   }
+  // 16-bit-output epilogues do their math in the TMEM-load layout (lane = row) and transpose the PACKED 16-bit tile: half the
+  // shared-memory traffic of staging fp32 (measured: with no epilogue at all the mainloops run at 1450-1600 TFLOP/s, the
+  // fp32-staged epilogues cost 22 % (qkv) / 30 % (fc1) -- they compete with TMA fills and UMMA operand reads for smem bandwidth)
+  constexpr bool kPacked16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || kLnConsumer);
+  constexpr bool kTmaStore16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || kLnConsumer);   // single 16-bit output, no row remap
+  float lane_r = 0.f, lane_mr = 0.f;   // LN consumer: rstd and -mean * rstd of row m0 + lane
+  if constexpr (kLnConsumer) {
+    if (m0 + lane < p.M) {
+      const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * long(m0 + lane));
+      lane_r = st.x;
+      lane_mr = st.y;
+    }
+  }
   load_resid(0);
   const uint32_t stg_s = smem_u32(stg);
   // bias of the next chunk is fetched while the current one is processed (its L2 / L1 latency sat on the first FADD of every chunk)
@@ -203,6 +216,9 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
   if (p.bias != nullptr && nchunks > 0) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + c4 * 4));
   mbar_wait(tfull, aphase);
   tc_fence_after();
+#ifdef GEMM_DIAG_NOEPI   // timing diagnostic: mainloop only (outputs are not written)
+  nchunks = 0;
+#endif
   if (nchunks == 0) {
     tc_fence_before();
     __syncwarp();
@@ -218,6 +234,81 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
       tc_fence_before();
       __syncwarp();
       if (lane == 0) release_tmem();   // one arrival per warp: 8 (16 for a CTA pair, half of them remote) instead of 256 (512)
+    }
+    if constexpr (kPacked16) {
+      // lane = row: bias / fold vectors are warp-uniform (broadcast) loads; results are packed to 16 bits, written to a
+      // [32 rows x 64 B] tile (16-byte slots XOR-swizzled by (row >> 1) & 3: conflict-free both ways) and read back so that
+      // 4 lanes cover one row's 64 contiguous bytes (a warp instruction stores 8 full row segments).
+      uint32_t o16[16], pre16[16];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j));
+        float4 a = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+        if constexpr (kLnConsumer) {   // finish the LayerNorm: rstd * acc - rstd * mean * (W gamma) + (W beta + b)
+          const float4 gg = __ldg(reinterpret_cast<const float4*>(p.ln_vec + n + 4 * j));
+          a.x = fmaf(a.x, lane_r, fmaf(lane_mr, gg.x, bb.x)); a.y = fmaf(a.y, lane_r, fmaf(lane_mr, gg.y, bb.y));
+          a.z = fmaf(a.z, lane_r, fmaf(lane_mr, gg.z, bb.z)); a.w = fmaf(a.w, lane_r, fmaf(lane_mr, gg.w, bb.w));
+        } else {
+          a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
+        }
+        if constexpr (EPI == EPI_GELU16_SAVE) { pre16[2 * j] = O::pack(a.x, a.y); pre16[2 * j + 1] = O::pack(a.z, a.w); }
+        if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELU16_LN) {
+          a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
+        }
+        o16[2 * j] = O::pack(a.x, a.y);
+        o16[2 * j + 1] = O::pack(a.z, a.w);
+      }
+      if constexpr (kTmaStore16) {
+        // The tile leaves through the TMA store engine: two 32-column chunks form a [32 rows x 128 B] SWIZZLE_128B tile in the
+        // staging buffer, one elected lane issues cp.async.bulk.tensor (full 128-byte lines, rows beyond M clipped by the
+        // tensor map).  Measured before: of the 0.062 ms the qkv epilogue added to a 0.242 ms mainloop, 0.048 ms were the
+        // LSU global stores themselves (0.043 of 0.132 ms for fc1).
+        const int half_sel = cc & 1;
+        if (half_sel == 0) {                       // staging tile free again? (reads of the previous TMA store done)
+          if (lane == 0) tma_store_wait_read<0>();
+          __syncwarp();
+        }
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          sts_v4(stg_s + lane * 128 + ((uint32_t(half_sel * 4 + q4) ^ uint32_t(lane & 7)) << 4), o16[4 * q4], o16[4 * q4 + 1], o16[4 * q4 + 2], o16[4 * q4 + 3]);
+        if (half_sel == 1 || cc == nchunks - 1) {
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(tmap_c, stg, n - 32 * half_sel, m0);   // columns beyond N / rows beyond M are clipped
+            tma_store_commit();
+          }
+        }
+        continue;
+      }
+      __syncwarp();            // previous chunk's staging reads are complete
+      const uint32_t wsw = uint32_t((lane >> 1) & 3);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        sts_v4(stg_s + lane * 64 + ((uint32_t(q4) ^ wsw) << 4), o16[4 * q4], o16[4 * q4 + 1], o16[4 * q4 + 2], o16[4 * q4 + 3]);
+        if constexpr (EPI == EPI_GELU16_SAVE)
+          sts_v4(stg_s + 2048 + lane * 64 + ((uint32_t(q4) ^ wsw) << 4), pre16[4 * q4], pre16[4 * q4 + 1], pre16[4 * q4 + 2], pre16[4 * q4 + 3]);
+      }
+      __syncwarp();
+      const int slot = lane & 3;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int rl = 8 * k + (lane >> 2);
+        const int m = m0 + rl;
+        const uint32_t off = uint32_t(rl * 64) + ((uint32_t(slot) ^ uint32_t((rl >> 1) & 3)) << 4);
+        const float4 w = lds_f4(stg_s + off);
+        if (m < p.M)
+          st_global_v4(reinterpret_cast<typename O::T*>(p.out) + long(m) * p.ld_out + n + 8 * slot, __float_as_uint(w.x), __float_as_uint(w.y),
+                       __float_as_uint(w.z), __float_as_uint(w.w));
+        if constexpr (EPI == EPI_GELU16_SAVE) {
+          const float4 wp = lds_f4(stg_s + 2048 + off);
+          if (m < p.M)
+            st_global_v4(reinterpret_cast<typename O::T*>(p.aux16) + long(m) * p.ld_out + n + 8 * slot, __float_as_uint(wp.x), __float_as_uint(wp.y),
+                         __float_as_uint(wp.z), __float_as_uint(wp.w));
+        }
+      }
+      continue;
     }
     __syncwarp();              // previous chunk's staging reads are complete
 #pragma unroll
@@ -326,7 +417,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, uint8
 template <int DT, int EPI, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg_base = smem + GEMM_STAGES * GEMM_STAGE_BYTES;
@@ -447,9 +538,10 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int m0 = (tile / num_n) * GEMM_BM + q * 32;
       const int n0 = (tile % num_n) * GEMM_BN + half * 128;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN + half * 128);
-      gemm_epilogue_subtile<DT, EPI>(p, stg, taddr, m0, n0, lane, &tfull_bar[as], aphase, [&]() { mbar_arrive(&tempty_bar[as]); });
+      gemm_epilogue_subtile<DT, EPI>(p, &tmap_c, stg, taddr, m0, n0, lane, &tfull_bar[as], aphase, [&]() { mbar_arrive(&tempty_bar[as]); });
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
+    if (lane == 0) tma_store_wait<0>();   // bulk stores of this warp (TMA-store epilogues) have landed before the CTA exits
   }
 
   tc_fence_before();
