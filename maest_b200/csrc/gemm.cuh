@@ -131,6 +131,9 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
   const int c4 = lane & 7;
   int nchunks = (p.N - n0 + 31) / 32;
   nchunks = nchunks < 0 ? 0 : (nchunks > 4 ? 4 : nchunks);
+  // Two epilogue organisations.  16-bit outputs (STORE16, GELU16, GELU16_SAVE, LN consumers): math in the TMEM-load layout, packed
+  // staging, TMA bulk store (kPacked16 below).  Everything else (fp32 outputs with residual / table reads, GELU backward,
+  // atomics): fp32 staging transpose so that all global traffic is row-coalesced.
   // RESID32: the residual tile does not depend on the accumulator, so its global loads are issued one chunk
   // ahead (and, for chunk 0, before waiting for the accumulator) to keep HBM requests in flight.
   // EPI_STORE32 is the only epilogue with an output-row remap (patch tokens -> packed token buffer).  The remap needs an
@@ -184,21 +187,10 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
   };
   constexpr bool kLnConsumer = (EPI == EPI_STORE16_LN || EPI == EPI_GELU16_LN);
   constexpr bool kLnProducer = (EPI == EPI_RESID32_LN);
-  float ln_r[kLnConsumer ? 8 : 1], ln_mr[kLnConsumer ? 8 : 1];   // rstd and -mean * rstd of this thread's 8 rows
-  if constexpr (kLnConsumer) {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      ln_r[i] = 0.f; ln_mr[i] = 0.f;
-      if (row_ok(i)) {
-        const float2 st = *reinterpret_cast<const float2*>(p.ln_stats + 2 * out_row(i));
-        ln_r[i] = st.x;
-        ln_mr[i] = st.y;
-      }
-    }
-  }
-  // 16-bit-output epilogues do their math in the TMEM-load layout (lane = row) and transpose the PACKED 16-bit tile: half the
-  // shared-memory traffic of staging fp32 (measured: with no epilogue at all the mainloops run at 1450-1600 TFLOP/s, the
-  // fp32-staged epilogues cost 22 % (qkv) / 30 % (fc1) -- they compete with TMA fills and UMMA operand reads for smem bandwidth)
+  // 16-bit-output epilogues do their math in the TMEM-load layout (lane = row) and transpose the PACKED 16-bit tile (half the
+  // shared-memory traffic of staging fp32).  Measured with experiment builds (tools/gemm_diag.py): with no epilogue at all the
+  // pair mainloops run at 1580-1600 TFLOP/s; reading the accumulator out of TMEM is free; for qkv the LSU global stores were
+  // 0.048 of the 0.062 ms the epilogue added (hence the TMA store), for fc1 the GELU math is 0.09 ms and the stores 0.045 ms.
   constexpr bool kPacked16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || kLnConsumer);
   constexpr bool kTmaStore16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || kLnConsumer);   // single 16-bit output, no row remap
   float lane_r = 0.f, lane_mr = 0.f;   // LN consumer: rstd and -mean * rstd of row m0 + lane
@@ -318,18 +310,13 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
     const float4 b4_cur = b4;
     if (p.bias != nullptr && cc + 1 < nchunks) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + col + 32));
     float4 g4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    if constexpr (kLnConsumer || kLnProducer) g4 = __ldg(reinterpret_cast<const float4*>(p.ln_vec + col));
+    if constexpr (kLnProducer) g4 = __ldg(reinterpret_cast<const float4*>(p.ln_vec + col));
     float4 acc4[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int rl = i * 4 + sub_row;
       float4 a = lds_f4(stg_s + rl * 128 + ((c4 ^ (rl & 7)) << 4));
-      if constexpr (kLnConsumer) {   // finish the LayerNorm: rstd * acc - rstd * mean * (W gamma) + (W beta + b)
-        a.x = fmaf(a.x, ln_r[i], fmaf(ln_mr[i], g4.x, b4_cur.x)); a.y = fmaf(a.y, ln_r[i], fmaf(ln_mr[i], g4.y, b4_cur.y));
-        a.z = fmaf(a.z, ln_r[i], fmaf(ln_mr[i], g4.z, b4_cur.z)); a.w = fmaf(a.w, ln_r[i], fmaf(ln_mr[i], g4.w, b4_cur.w));
-      } else {
-        a.x += b4_cur.x; a.y += b4_cur.y; a.z += b4_cur.z; a.w += b4_cur.w;
-      }
+      a.x += b4_cur.x; a.y += b4_cur.y; a.z += b4_cur.z; a.w += b4_cur.w;
       if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
       acc4[i] = a;
     }
@@ -359,36 +346,13 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       float4 a = acc4[i];
-      if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_LN) {
-        // no global read depends on the row here: do the math for every lane and predicate only the store (the per-row
-        // branch around the GELU cost a BSSY / BRA / BSYNC triple per row and chunk)
-        a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
-        if (row_ok(i)) {
-          uint2 o;
-          o.x = O::pack(a.x, a.y);
-          o.y = O::pack(a.z, a.w);
-          *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.out) + out_row(i) * p.ld_out + col) = o;
-        }
-        continue;
-      }
       if (!row_ok(i)) continue;
       const long r = out_row(i);
-      if constexpr (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELUBWD16 || kLnConsumer) {
-        if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELU16_LN) {
-          if constexpr (EPI == EPI_GELU16_SAVE) {   // training: keep the pre-activation for the backward pass
-            uint2 pre;
-            pre.x = O::pack(a.x, a.y);
-            pre.y = O::pack(a.z, a.w);
-            *reinterpret_cast<uint2*>(reinterpret_cast<typename O::T*>(p.aux16) + r * p.ld_out + col) = pre;
-          }
-          a.x = gelu_erf_fast(a.x); a.y = gelu_erf_fast(a.y); a.z = gelu_erf_fast(a.z); a.w = gelu_erf_fast(a.w);
-        }
-        if constexpr (EPI == EPI_GELUBWD16) {
-          const uint2 pre = *reinterpret_cast<const uint2*>(reinterpret_cast<const typename O::T*>(p.aux16) + r * p.ld_out + col);
-          const float2 u01 = O::unpack(pre.x), u23 = O::unpack(pre.y);
-          a.x *= gelu_erf_grad_fast(u01.x); a.y *= gelu_erf_grad_fast(u01.y);
-          a.z *= gelu_erf_grad_fast(u23.x); a.w *= gelu_erf_grad_fast(u23.y);
-        }
+      if constexpr (EPI == EPI_GELUBWD16) {
+        const uint2 pre = *reinterpret_cast<const uint2*>(reinterpret_cast<const typename O::T*>(p.aux16) + r * p.ld_out + col);
+        const float2 u01 = O::unpack(pre.x), u23 = O::unpack(pre.y);
+        a.x *= gelu_erf_grad_fast(u01.x); a.y *= gelu_erf_grad_fast(u01.y);
+        a.z *= gelu_erf_grad_fast(u23.x); a.w *= gelu_erf_grad_fast(u23.y);
         uint2 o;
         o.x = O::pack(a.x, a.y);
         o.y = O::pack(a.z, a.w);
