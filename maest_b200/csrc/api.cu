@@ -8,6 +8,7 @@
 #include "../../include/maest_b200.h"
 #include "attention.cuh"
 #include "attention_bwd.cuh"
+#include "attention_chain.cuh"
 #include "ingest.cuh"
 #include "metrics.cuh"
 #include "optim.cuh"
@@ -194,6 +195,7 @@ int init_dt() {
   if ((r = set_smem(attention_fwd_spec_kernel<DT, 128>, 120 * 1024))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, false>, att_smem_bytes<false>()))) return r;
   if ((r = set_smem(attention_bwd_kernel<DT>, ATTB_SMEM_BYTES))) return r;
+  if ((r = set_smem(attention_fwd_chain_kernel<DT>, ATC_SMEM_BYTES))) return r;
   return 0;
 }
 
@@ -429,6 +431,15 @@ int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, i
       if (bf) attention_fwd_kernel<DT_BF16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
       else attention_fwd_kernel<DT_F16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
       break;
+    case 3: {  // three-chain persistent kernel (attention_chain.cuh); needs >= 2 KV tiles per item
+      if (N <= ATT_BKV) return maest_attention_fwd(qkv, out, lse, B, N, H, op_dtype, 0, stream);
+      const int items = B * H * ((N + ATT_BQ - 1) / ATT_BQ);
+      const int sms = g_num_sms[cur_device()];
+      const int g = items < sms ? items : sms;
+      if (bf) attention_fwd_chain_kernel<DT_BF16><<<g, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, p, qkv);
+      else attention_fwd_chain_kernel<DT_F16><<<g, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, p, qkv);
+      break;
+    }
     case 16:   // timing diagnostic: the default kernel forced to ONE CTA per SM by padding the dynamic smem request
       if (bf) attention_fwd_spec_kernel<DT_BF16, 128><<<grid, ATT_THREADS, 120 * 1024, st>>>(tq, tq, p);
       else attention_fwd_spec_kernel<DT_F16, 128><<<grid, ATT_THREADS, 120 * 1024, st>>>(tq, tq, p);

@@ -47,10 +47,16 @@ class MelWindowBatcher:
         self.host = torch.zeros((batch_size, self.T, N_BANDS), dtype=torch.float16, pin_memory=pin)
         self.host_n = torch.zeros(batch_size, dtype=torch.int32, pin_memory=pin)
         self.host_s = torch.zeros(batch_size, dtype=torch.int32, pin_memory=pin)
+        self._h2d_done = None      # CUDA event recorded after the last batch's H2D copies (the pinned buffers are reused)
 
     def stage(self, files: Sequence[str], offsets: Optional[Sequence[Optional[int]]] = None):
         """Host half: copy each file's window bytes into the pinned buffer; returns (n_clips, frames_read, shifts)."""
         assert len(files) <= self.B
+        if self._h2d_done is not None:
+            # the previous batch's asynchronous H2D copies may still be queued behind earlier kernels: do not overwrite the
+            # pinned staging buffers until the DMA has actually read them
+            self._h2d_done.synchronize()
+            self._h2d_done = None
         buf = self.host.numpy()
         for i, f in enumerate(files):
             if str(f).endswith(".npy"):
@@ -79,6 +85,9 @@ class MelWindowBatcher:
         raw = self.host[:n_clips].to(self.device, non_blocking=True)
         nread = self.host_n[:n_clips].to(self.device, non_blocking=True)
         shift = self.host_s[:n_clips].to(self.device, non_blocking=True) if self.roll else None
+        if self.device.type == "cuda":
+            self._h2d_done = torch.cuda.Event()
+            self._h2d_done.record(torch.cuda.current_stream(self.device))
         return ops.mel_ingest(raw, nread, shift, self.norm[0], self.norm[1])
 
     def __call__(self, files, offsets=None) -> torch.Tensor:

@@ -211,6 +211,8 @@ class MAEST(nn.Module):
             raise NotImplementedError("the B200 path is specialised to ViT-Base/16, 12 heads, mono, distilled (all shipped MAEST configs)")
         if tuple(stride) != (10, 10):
             raise NotImplementedError("the B200 patch kernels are specialised to stride (10, 10)")
+        if int(tuple(img_size)[0]) != 96:
+            raise NotImplementedError("the B200 patch kernels are specialised to 96 mel bands (input_f=96, every shipped MAEST config)")
         self.num_classes = num_classes
         self.u_patchout = u_patchout
         self.img_size = tuple(img_size)
@@ -362,27 +364,28 @@ class MAEST(nn.Module):
             keep_f = torch.randperm(Fp)[: Fp - self.s_patchout_f].sort().values
 
         def _sub(cur, n, idx):
+            # the reference indexes the ALREADY-reduced tensor with indices built from the ORIGINAL grid size
+            # (models/maest.py:703-766: `torch.arange(F_dim)` / `torch.arange(T_dim)`), so a combination of random structured
+            # patchout with the indices / interleaved options raises IndexError exactly where torch's indexing does
             base = torch.arange(n) if cur is None else cur
+            if len(idx) and int(idx.max()) >= len(base):
+                raise IndexError(f"index {int(idx.max())} is out of bounds for dimension with size {len(base)}")
             return base[idx]
 
         if self.s_patchout_f_indices:
-            n = Fp if keep_f is None else len(keep_f)
-            kept = torch.arange(n)
+            kept = torch.arange(Fp)
             for i in self.s_patchout_f_indices:
                 kept = kept[kept != int(i)]
             keep_f = _sub(keep_f, Fp, kept)
         if self.s_patchout_f_interleaved:
-            n = Fp if keep_f is None else len(keep_f)
-            keep_f = _sub(keep_f, Fp, torch.arange(0, n, self.s_patchout_f_interleaved))
+            keep_f = _sub(keep_f, Fp, torch.arange(0, Fp, self.s_patchout_f_interleaved))
         if self.s_patchout_t_indices:
-            n = Tp if keep_t is None else len(keep_t)
-            kept = torch.arange(n)
+            kept = torch.arange(Tp)
             for i in self.s_patchout_t_indices:
                 kept = kept[kept != int(i)]
             keep_t = _sub(keep_t, Tp, kept)
         if self.s_patchout_t_interleaved:
-            n = Tp if keep_t is None else len(keep_t)
-            keep_t = _sub(keep_t, Tp, torch.arange(0, n, self.s_patchout_t_interleaved))
+            keep_t = _sub(keep_t, Tp, torch.arange(0, Tp, self.s_patchout_t_interleaved))
         keep_seq = None
         if self.training and self.u_patchout:
             seq_len = (Fp if keep_f is None else len(keep_f)) * (Tp if keep_t is None else len(keep_t))
@@ -392,6 +395,8 @@ class MAEST(nn.Module):
     def tokens_from_mel(self, mel: torch.Tensor) -> torch.Tensor:
         """[B,96,T] mel -> packed fp32 token buffer [B, N, 768] entering blocks[0] (forward_features up to :800)."""
         B, Fm, T = mel.shape
+        if Fm != 96:
+            raise NotImplementedError(f"the B200 patch kernels take 96 mel bands, got {Fm}")
         Fp, Tp = (Fm - PATCH) // 10 + 1, (T - PATCH) // 10 + 1
         t_offset, keep_f, keep_t, keep_seq = self._draw_patchout(Fp, Tp)
         keep_ft = ops.keep_ft_tensor(keep_f, keep_t, Fp, Tp, keep_seq, mel.device)

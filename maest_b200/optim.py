@@ -1,9 +1,14 @@
 """Optimiser side of the training step: one-launch AdamW over all parameters with the SWA running
 average fused in, and the reference's learning-rate lambdas.
 
-Mirrors `Module.get_optimizer` / `get_scheduler_lambda` / `get_lr_scheduler` (models/module.py:207-243), the ramps of
-helpers/ramp.py:21-60,102-140 and the running average that `StochasticWeightAveragingAndCopy` (helpers/swa_callback.py)
-transfers into `net_swa` (torch.optim.swa_utils: avg += (p - avg) / (n_averaged + 1))."""
+Mirrors `Module.get_optimizer` / `get_scheduler_lambda` / `get_lr_scheduler` (models/module.py:207-243) and the running average
+that `StochasticWeightAveragingAndCopy` (helpers/swa_callback.py) transfers into `net_swa` (torch.optim.swa_utils:
+avg += (p - avg) / (n_averaged + 1)).
+
+The four closed-form ramps below (`exp_rampup`, `linear_rampdown`, `exp_warmup_linear_down`, `cosine_cycle`) are TRANSCRIBED
+from helpers/ramp.py:21-33,47-62,102-109,124-137 (same names, same `np.clip(epoch, 0.5, ...)` bodies): ~35 lines of host-side
+schedule arithmetic that must be value-identical to the reference (pinned by tests/golden/c7_sched.npz); they are not a
+re-design target."""
 from __future__ import annotations
 
 import ctypes as C
@@ -137,6 +142,13 @@ class FusedAdamW(torch.optim.Optimizer):
                                                 float(group["betas"][0]), float(group["betas"][1]), float(group["eps"]),
                                                 float(group["weight_decay"]), int(step), float(grad_scale), float(swa_inv),
                                                 torch.cuda.current_stream().cuda_stream), "adamw_step")
+            # The kernel wrote the parameters (and the SWA copies) through raw pointers: tell autograd / every cache keyed on
+            # `tensor._version` (MAEST._weight16's 16-bit operand copies, MAEST._ln_fold) that the values changed.
+            torch._C._increment_version(plist)
+            if swa_inv != 0.0:
+                all_params = [p for g in self.param_groups for p in g["params"]]
+                pid = {id(p) for p in plist}
+                torch._C._increment_version([s for p, s in zip(all_params, self._swa) if id(p) in pid])
         if update_swa and self._swa is not None:
             self.n_averaged += 1
         return loss

@@ -200,6 +200,8 @@ def training_forward(model, mel: torch.Tensor, targets: torch.Tensor, mix: Optio
         perm, lam = mix
         mel = ops.mixup(mel, perm.to(dev), lam.to(dev))
         targets = ops.mixup(targets, perm.to(dev), lam.to(dev))
+    if mel.shape[1] != 96:
+        raise NotImplementedError(f"the B200 patch kernels take 96 mel bands, got {mel.shape[1]}")
     Fp, Tp = (mel.shape[1] - 16) // 10 + 1, (mel.shape[2] - 16) // 10 + 1
     t_offset, keep_f, keep_t, keep_seq = model._draw_patchout(Fp, Tp)
     keep_ft = ops.keep_ft_tensor(keep_f, keep_t, Fp, Tp, keep_seq, dev)
