@@ -83,6 +83,11 @@ int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t w
 int32_t maest_adamw_step(const void* tensor_table, const void* chunk_table, int32_t n_chunks, float lr, float beta1, float beta2,
                          float eps, float weight_decay, int32_t step, float grad_scale, float swa_inv, void* stream);
 
+/* Epoch-end weight averaging without a second model copy: for every tensor of the table (same layout as above; only p, swa and
+ * n are read) swa += (p - swa) * swa_inv.  Replaces AveragedModel.update_parameters as driven by Lightning's
+ * StochasticWeightAveraging / helpers/swa_callback.py:11-17 (the averaged model IS net_swa here). */
+int32_t maest_swa_fold(const void* tensor_table, const void* chunk_table, int32_t n_chunks, float swa_inv, void* stream);
+
 /* Validation metrics on the device.  Replaces sklearn's average_precision_score / roc_auc_score
  * (average=None) as called by Module.on_test_validation_epoch_end, models/module.py:189-190, on host copies of the gathered
  * predictions.  score_sorted / label_sorted: fp32 [n, C], every class column ordered by descending score (labels re-ordered
@@ -224,6 +229,16 @@ int32_t maest_head_bwd(const float* x, int32_t B, int32_t N, const float* dlogit
                        const float* norm_b, const float* head_ln_w, const float* head_ln_b, const float* head_w, int32_t C,
                        float* dx, float* hz_ws, float* d_norm_w, float* d_norm_b, float* d_head_ln_w, float* d_head_ln_b,
                        float* d_head_w, float* d_head_b, void* stream);
+
+/* The same for distilled_type = "separated" (models/maest.py:914-925: logits = head(cls), logits_dist = head_dist(dist); the
+ * teacher-student step of models/module.py:279-313 trains both): dlogits / dlogits_dist are the two BCE gradients, z1_ws is a
+ * second fp32 [B,768] scratch, head_dist is a bare Linear. */
+int32_t maest_head_bwd_separated(const float* x, int32_t B, int32_t N, const float* dlogits, const float* dlogits_dist,
+                                 const float* gscale, const float* norm_w, const float* norm_b, const float* head_ln_w,
+                                 const float* head_ln_b, const float* head_w, const float* head_dist_w, int32_t C, float* dx,
+                                 float* hz_ws, float* z1_ws, float* d_norm_w, float* d_norm_b, float* d_head_ln_w,
+                                 float* d_head_ln_b, float* d_head_w, float* d_head_b, float* d_head_dist_w, float* d_head_dist_b,
+                                 void* stream);
 
 /* LayerNorm backward (autograd of norm1 / norm2): dx += LN'(dy); dgamma/dbeta accumulated; optional op16 copy of the updated dx. */
 int32_t maest_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,

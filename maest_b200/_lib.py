@@ -16,7 +16,7 @@ c_void_p, c_int32, c_int64, c_size_t, c_float = C.c_void_p, C.c_int32, C.c_int64
 F16, BF16, F32 = 0, 1, 2
 EPI_STORE16, EPI_GELU16, EPI_RESID32, EPI_STORE32, EPI_GELUBWD16, EPI_ATOMIC32 = 0, 1, 2, 3, 4, 5
 EPI_STORE16_LN, EPI_GELU16_LN, EPI_RESID32_LN = 7, 8, 9
-ABI_VERSION = 6
+ABI_VERSION = 7
 HEAD_MEAN, HEAD_SEPARATED = 0, 1
 
 
@@ -34,6 +34,7 @@ SIGNATURES = {
     "maest_logmel_raw16_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
     "maest_mel_ingest_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p]),
     "maest_adamw_step": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_float, c_float, c_float, c_float, c_int32, c_float, c_float, c_void_p]),
+    "maest_swa_fold": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_void_p]),
     "maest_ap_roc_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "maest_patch_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "maest_patch_tokens_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
@@ -55,6 +56,7 @@ SIGNATURES = {
     "maest_mixup_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),
     "maest_bce_logits_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "maest_head_bwd": (c_int32, [c_void_p, c_int32, c_int32] + [c_void_p] * 7 + [c_int32] + [c_void_p] * 9),
+    "maest_head_bwd_separated": (c_int32, [c_void_p, c_int32, c_int32] + [c_void_p] * 9 + [c_int32] + [c_void_p] * 12),
     "maest_layernorm_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
     "maest_colsum": (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "maest_cast_rows16": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),

@@ -195,7 +195,8 @@ int init_dt() {
   if ((r = set_smem(attention_fwd_spec_kernel<DT, 128>, 120 * 1024))) return r;
   if ((r = set_smem(attention_fwd_kernel<DT, false>, att_smem_bytes<false>()))) return r;
   if ((r = set_smem(attention_bwd_kernel<DT>, ATTB_SMEM_BYTES))) return r;
-  if ((r = set_smem(attention_fwd_chain_kernel<DT>, ATC_SMEM_BYTES))) return r;
+  if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg3>, AtcCfg3::SMEM_BYTES))) return r;
+  if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg4>, AtcCfg4::SMEM_BYTES))) return r;
   return 0;
 }
 
@@ -204,7 +205,7 @@ int init_dt() {
 extern "C" {
 
 const char* maest_last_error(void) { return g_err; }
-int32_t maest_abi_version(void) { return 6; }
+int32_t maest_abi_version(void) { return 7; }
 
 int32_t maest_init(int32_t device) {
   if (device < 0 || device >= 64) return fail(-1, "bad device %d", device);
@@ -270,6 +271,14 @@ int32_t maest_adamw_step(const void* tensor_table, const void* chunk_table, int3
   a.bias_c2_sqrt = float(sqrt(1.0 - pow(double(beta2), double(step))));
   a.grad_scale = grad_scale; a.swa_inv = swa_inv;
   adamw_multi_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(a);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_swa_fold(const void* tensor_table, const void* chunk_table, int32_t n_chunks, float swa_inv, void* stream) {
+  if (n_chunks <= 0) return 0;
+  swa_fold_multi_kernel<<<n_chunks, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const OptTensor*>(tensor_table),
+                                                                     reinterpret_cast<const OptChunk*>(chunk_table), swa_inv);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -431,13 +440,23 @@ int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, i
       if (bf) attention_fwd_kernel<DT_BF16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
       else attention_fwd_kernel<DT_F16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
       break;
-    case 3: {  // three-chain persistent kernel (attention_chain.cuh); needs >= 2 KV tiles per item
-      if (N <= ATT_BKV) return maest_attention_fwd(qkv, out, lse, B, N, H, op_dtype, 0, stream);
+    case 3:    // chains kernel, 3 chains x 128 keys (attention_chain.cuh); needs >= 2 KV tiles per item
+    case 4: {  // chains kernel, 4 chains x 96 keys
+      const int bkv = variant == 3 ? AtcCfg3::BKV : AtcCfg4::BKV;
+      const int nkv_max = variant == 3 ? AtcCfg3::NKV_MAX : AtcCfg4::NKV_MAX;
+      if (N <= bkv || (N + bkv - 1) / bkv > nkv_max) return maest_attention_fwd(qkv, out, lse, B, N, H, op_dtype, 0, stream);
       const int items = B * H * ((N + ATT_BQ - 1) / ATT_BQ);
       const int sms = g_num_sms[cur_device()];
       const int g = items < sms ? items : sms;
-      if (bf) attention_fwd_chain_kernel<DT_BF16><<<g, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, p, qkv);
-      else attention_fwd_chain_kernel<DT_F16><<<g, ATC_THREADS, ATC_SMEM_BYTES, st>>>(tq, p, qkv);
+      CUtensorMap tkv;
+      if ((r = make_tmap(&tkv, qkv, op_dtype, uint64_t(B) * N, uint64_t(3) * H * ATT_D, uint64_t(3) * H * ATT_D, bkv))) return r;
+      if (variant == 3) {
+        if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg3><<<g, AtcCfg3::THREADS, AtcCfg3::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+        else attention_fwd_chain_kernel<DT_F16, AtcCfg3><<<g, AtcCfg3::THREADS, AtcCfg3::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+      } else {
+        if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg4><<<g, AtcCfg4::THREADS, AtcCfg4::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+        else attention_fwd_chain_kernel<DT_F16, AtcCfg4><<<g, AtcCfg4::THREADS, AtcCfg4::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+      }
       break;
     }
     case 16:   // timing diagnostic: the default kernel forced to ONE CTA per SM by padding the dynamic smem request
@@ -658,9 +677,31 @@ int32_t maest_head_bwd(const float* x, int32_t B, int32_t N, const float* dlogit
   p.x = x; p.N = N; p.dlogits = dlogits; p.gscale = gscale; p.norm_w = norm_w; p.norm_b = norm_b; p.hln_w = head_ln_w;
   p.hln_b = head_ln_b; p.head_w = head_w; p.C = C; p.dx = dx; p.hz = hz_ws; p.d_norm_w = d_norm_w; p.d_norm_b = d_norm_b;
   p.d_hln_w = d_head_ln_w; p.d_hln_b = d_head_ln_b;
+  p.separated = 0; p.dlogits_dist = nullptr; p.hdist_w = nullptr; p.z1out = nullptr;
   cudaStream_t st = (cudaStream_t)stream;
   head_bwd_clip_kernel<<<B, 256, 0, st>>>(p);
   head_wgrad_kernel<<<C, 256, 0, st>>>(dlogits, gscale, hz_ws, B, C, d_head_w, d_head_b);
+  CUDA_OK(cudaGetLastError());
+  return 0;
+}
+
+int32_t maest_head_bwd_separated(const float* x, int32_t B, int32_t N, const float* dlogits, const float* dlogits_dist,
+                                 const float* gscale, const float* norm_w, const float* norm_b, const float* head_ln_w,
+                                 const float* head_ln_b, const float* head_w, const float* head_dist_w, int32_t C, float* dx,
+                                 float* hz_ws, float* z1_ws, float* d_norm_w, float* d_norm_b, float* d_head_ln_w,
+                                 float* d_head_ln_b, float* d_head_w, float* d_head_b, float* d_head_dist_w, float* d_head_dist_b,
+                                 void* stream) {
+  if (B <= 0) return 0;
+  if (C > 1024) return fail(-1, "head_bwd_separated: at most 1024 classes");
+  HeadBwdParams p;
+  p.x = x; p.N = N; p.dlogits = dlogits; p.gscale = gscale; p.norm_w = norm_w; p.norm_b = norm_b; p.hln_w = head_ln_w;
+  p.hln_b = head_ln_b; p.head_w = head_w; p.C = C; p.dx = dx; p.hz = hz_ws; p.d_norm_w = d_norm_w; p.d_norm_b = d_norm_b;
+  p.d_hln_w = d_head_ln_w; p.d_hln_b = d_head_ln_b;
+  p.separated = 1; p.dlogits_dist = dlogits_dist; p.hdist_w = head_dist_w; p.z1out = z1_ws;
+  cudaStream_t st = (cudaStream_t)stream;
+  head_bwd_clip_kernel<<<B, 256, 0, st>>>(p);
+  head_wgrad_kernel<<<C, 256, 0, st>>>(dlogits, gscale, hz_ws, B, C, d_head_w, d_head_b);
+  head_wgrad_kernel<<<C, 256, 0, st>>>(dlogits_dist, gscale, z1_ws, B, C, d_head_dist_w, d_head_dist_b);
   CUDA_OK(cudaGetLastError());
   return 0;
 }

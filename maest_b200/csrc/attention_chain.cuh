@@ -1,30 +1,31 @@
-// Attention forward, "three chains" kernel (round 2 default) for sm_100a: persistent, one CTA per SM, d_head = 64.
+// Attention forward, "chains" kernel (round-2 default) for sm_100a: persistent, one CTA per SM, d_head = 64.
 //
 // Replaces models/maest.py:362-375 like attention.cuh; same inputs / outputs (packed qkv activation in, o16 and the optional
 // log-sum-exp out).  What changed against attention_fwd_spec_kernel, and why (profiles/r01_attention_phase_clocks.md: that
 // kernel was bound by the per-tile dependency chain S ready -> tcgen05.ld -> exp -> tcgen05.st -> PV with ONE softmax warp per
 // sub-partition and CTA, 4.5 issue slots + one MUFU op per score):
 //   * a work item is one 128-query tile of one (clip, head); a CTA walks items blockIdx.x, +gridDim.x, ... and its KV tiles form
-//     ONE continuous stream g = 0, 1, 2, ...; tile g belongs to chain g % 3.  Each chain has its own 128-column score buffer
-//     in TMEM and its own 4 softmax warps, so every sub-partition always has three softmax warps in different phases; the
-//     next item's Q / K / V loads and first QK^T overlap the previous item's tail (no per-CTA prologue bubble).
-//   * P is written IN PLACE over the scores it came from (16-bit pairs over the first 64 columns of the chain's buffer), the
-//     tensor pipe runs PV(g) and then QK^T(g+3) into the same buffer in issue order; the O accumulator is double-buffered
-//     across items (TMEM: 3 x 128 + 2 x 64 = 512 columns).
+//     ONE continuous stream g = 0, 1, 2, ...; tile g belongs to chain g % NCH.  Each chain has its own score buffer in TMEM and
+//     its own 4 softmax warps, so every sub-partition always has NCH softmax warps in different phases; the next item's
+//     Q / K / V loads and first QK^T overlap the previous item's tail (no per-CTA prologue bubble).
+//   * P is written IN PLACE over the scores it came from (16-bit pairs over the first half of the chain's buffer); PV(g) reads
+//     it there and QK^T(g + NCH) refills the buffer; the O accumulator is double-buffered across items
+//     (TMEM: NCH x BKV + 2 x 64 = 512 columns for 3 x 128 and for 4 x 96).
 //   * the softmax never touches O: every tile of an item is exponentiated against ONE reference m_ref = the exact row max of
 //     the item's first KV tile (published through shared memory by the chain that owns that tile).  No running max, no
 //     rescaling, no per-tile wait on the previous PV.  P may exceed 1: fp16 P holds 2^a exactly up to a < 16 and fp32
 //     accumulators do not care about the common scale.  Rows for which that is not enough (a 16-bit P overflowed to inf, the
-//     row sum overflowed, or a polynomial-path exponent left [-126, 126]) are DETECTED in the epilogue (non-finite O or l)
-//     and recomputed exactly by the epilogue warp on the CUDA cores (att_row_exact) -- a rare path, but it makes the kernel
-//     correct for any input (tests: test_attention_sharp_scores_and_rescale_path).
+//     row sum overflowed, or a polynomial-path exponent left [-126, 126]) are DETECTED in the epilogue (non-finite O or l),
+//     flagged with a NaN sentinel and recomputed exactly on the CUDA cores after the main loop (att_row_exact) -- a rare path,
+//     but it makes the kernel correct for any input (tests: test_attention_sharp_scores_and_rescale_path).
 //   * per PAIR of scores: one FFMA2 (scale and shift, packed fp32x2), two MUFU.EX2, one FADD2 (row sum), one F2FP; ATT_CHAIN_NPOLY
 //     of every 8 pairs take the exponential on the FMA pipe instead (Cody-Waite + degree-3 minimax polynomial, relative error
 //     8.0e-5, packed fp32x2 ops) because MUFU (16 / clk / SM) is the binding unit at d_head = 64.
-// Warp roles (512 threads): warps 0-11 softmax (chain = warp / 4, TMEM lane quadrant = warp % 4), 12 TMA producer, 13 MMA
-// issuer, 14-15 idle (they complete the fourth warpgroup so that setmaxnreg can move its registers to the softmax warps).  The epilogue of an item (O / l -> 16-bit, log-sum-exp, exact redo) is done by the chain that owns the SECOND tile
-// after the item's last one, right after it has finished that tile: by then the item's last PV has retired, so the chain
-// never waits for the tensor pipe, and no extra warps (and their registers) are needed.  Requires >= 2 KV tiles per item.
+// Warp roles: 4 x NCH softmax warps (chain = warp / 4, TMEM lane quadrant = warp % 4), then one warpgroup of helpers: TMA
+// producer, PV issuer, QK^T issuer, one idle warp (completes the warpgroup so that setmaxnreg can move its registers to the
+// softmax warps).  The epilogue of an item (O / l -> 16-bit, log-sum-exp) is done by the chain that owns the SECOND tile after
+// the item's last one, right after it has finished that tile: by then the item's last PV has retired, so the chain never waits
+// for the tensor pipe.  Requires >= 2 KV tiles per item (api.cu falls back to attention_fwd_spec_kernel below that).
 #pragma once
 #include "attention.cuh"
 
@@ -34,25 +35,30 @@ namespace mb {
 #define ATT_CHAIN_NPOLY 3     // pairs of every 8 whose exponentials run on the FMA pipe
 #endif
 
-constexpr int ATC_THREADS = 512;   // 16 warps: the register file is handed out per warpgroup (setmaxnreg)
-// 512 threads launch with 128 registers each (the whole file).  The producer / issuer warpgroup gives most of its share back
-// (setmaxnreg.dec) and the three softmax warpgroups take it (setmaxnreg.inc): 3 x 128 x 152 + 128 x 56 = 65 536.  At 128 registers
-// the softmax loop spilled its row-sum accumulators to local memory, and with ~200 KB of shared memory configured the L1 that
-// backs local memory is only ~30 KB: every cold-path spill reload went to L2 (measured: a 150-instruction epilogue took 5000 cycles).
-constexpr int ATC_REGS_SOFTMAX = 152;
-constexpr int ATC_REGS_AUX = 56;
-#ifndef ATC_R_N
-#define ATC_R_N 5
-#endif
-constexpr int ATC_R = ATC_R_N;          // ring slots, each {K tile, V tile} = 32 KB
-constexpr int ATC_NBAR = 2 + 2 + 2 * ATC_R + 3 + 3 + 2 + 2 + 2 + 2;
-constexpr int ATC_OFF_KV = 2 * ATT_TILE_BYTES;
-constexpr int ATC_OFF_BAR = ATC_OFF_KV + ATC_R * 2 * ATT_TILE_BYTES;
-constexpr int ATC_OFF_MREF = ATC_OFF_BAR + ((ATC_NBAR * 8 + 16 + 127) / 128) * 128;
-constexpr int ATC_OFF_LPART = ATC_OFF_MREF + 2 * 128 * 4;
-constexpr int ATC_SMEM_BYTES = ATC_OFF_LPART + 2 * 3 * 128 * 4;
+// NCH chains x BKV keys per tile; CW = score columns per tcgen05.ld chunk; R = ring slots of {K tile, V tile}.
+// Registers: the CTA launches with the whole file split evenly, the helper warpgroup gives most of its share back
+// (setmaxnreg.dec) and the softmax warpgroups take it (setmaxnreg.inc).  With spills the kernel was 30 % slower: the L1 that
+// backs local memory is only ~30 KB when ~200 KB of shared memory are configured, so spill reloads went to L2.
+template <int NCH_, int BKV_, int CW_, int R_, int REGS_SM_, int REGS_AUX_, int NKV_MAX_>
+struct AtcCfgT {
+  static constexpr int NCH = NCH_, BKV = BKV_, CW = CW_, R = R_, REGS_SM = REGS_SM_, REGS_AUX = REGS_AUX_;
+  static constexpr int THREADS = (4 * NCH + 4) * 32;
+  static constexpr int KV_BYTES = BKV * ATT_D * 2;
+  static constexpr int SLOT_BYTES = 2 * KV_BYTES;
+  static constexpr int NBAR = 2 + 2 + 2 * R + 3 * NCH + 2 + 2 + 2 + 2;
+  static constexpr int OFF_KV = 2 * ATT_TILE_BYTES;
+  static constexpr int OFF_BAR = OFF_KV + R * SLOT_BYTES;
+  static constexpr int OFF_MREF = OFF_BAR + ((NBAR * 8 + 16 + 127) / 128) * 128;
+  static constexpr int OFF_LPART = OFF_MREF + 2 * 128 * 4;
+  static constexpr int NKV_MAX = NKV_MAX_;      // KV tiles per item the per-tile row-sum slots are sized for
+  static constexpr int SMEM_BYTES = OFF_LPART + 2 * NKV_MAX * 128 * 4;
+  static_assert(NCH * BKV + 128 <= 512, "TMEM: NCH score buffers + two O accumulators");
+  static_assert(BKV % 32 == 0 && (CW == 32 || CW == 16), "tile / chunk shape");
+};
+using AtcCfg3 = AtcCfgT<3, 128, 32, 5, 152, 56, 24>;     // 512 threads: 3 x 128 x 152 + 128 x 56 = 65 536 registers
+using AtcCfg4 = AtcCfgT<4, 96, 16, 6, 104, 56, 32>;      // 640 threads: 4 x 128 x 104 + 128 x 56 = 60 416 registers
 
-#ifdef ATC_DIAG   // timing diagnostic: per-role wait clocks, written over p.lse[blockIdx.x * 128 + ...] (results of lse are garbage)
+#ifdef ATC_DIAG   // timing diagnostic: per-role wait clocks, written over p.lse[blockIdx.x * 512 + ...] (the lse values are garbage)
 #define ATC_T0() unsigned t__ = (unsigned)clock()
 #define ATC_ACC(var) do { const unsigned n__ = (unsigned)clock(); var += n__ - t__; t__ = n__; } while (0)
 #else
@@ -68,23 +74,41 @@ __device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.
 __device__ __forceinline__ u64 f2_add(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 __device__ __forceinline__ u64 f2_sub(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
-// The values a tcgen05.ld wrote become visible at tcgen05.wait::ld; this empty asm makes every later use depend on a point
-// AFTER the wait (the loads are software-pipelined, so there is real work between the ld and its wait).
-__device__ __forceinline__ void reg_fence32(uint32_t (&r)[32]) {
-  asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
-               "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
-  asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
-               "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
-}
-
-__device__ __forceinline__ void tmem_st16_lo(uint32_t taddr, const uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
-      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
-      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
-      "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-      : "memory");
-}
+// A chunk of W score columns of one TMEM lane in registers.  ld() is asynchronous: the values are defined after
+// tcgen05.wait::ld + fence() (the empty asm makes every later use depend on a point AFTER the wait; the loads are
+// software-pipelined, so there is real work between a ld and its wait).  st_lo() stores the first W/2 words (the packed P).
+template <int W> struct AtcChunk;
+template <> struct AtcChunk<32> {
+  uint32_t r[32];
+  __device__ __forceinline__ void ld(uint32_t taddr) { tmem_ld32(taddr, r); }
+  __device__ __forceinline__ void fence() {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+    asm volatile("" : "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                 "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31]));
+  }
+  __device__ __forceinline__ void st_lo(uint32_t taddr) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+        : "memory");
+  }
+};
+template <> struct AtcChunk<16> {
+  uint32_t r[16];
+  __device__ __forceinline__ void ld(uint32_t taddr) { tmem_ld16(taddr, r); }
+  __device__ __forceinline__ void fence() {
+    asm volatile("" : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+  }
+  __device__ __forceinline__ void st_lo(uint32_t taddr) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
+                 "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+  }
+};
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
 }
@@ -103,39 +127,34 @@ __device__ __forceinline__ void mma_qk4(uint32_t tS, uint64_t qd, uint64_t kd, u
       "tcgen05.mma.cta_group::1.kind::f16 [%0], q3, k3, %3, p1;\n\t}\n" ::"r"(tS), "l"(qd), "l"(kd), "r"(idesc)
       : "memory");
 }
-// O[tO] (+)= P[tP] V: eight K = 16 steps (P advances 8 TMEM columns, V 16 rows = 2048 B = +128 per step); acc0 = 0 starts a new item.
-__device__ __forceinline__ void mma_pv8(uint32_t tO, uint32_t tP, uint64_t vd, uint32_t idesc, uint32_t acc0) {
-  asm volatile(
-      "{\n\t.reg .pred p0, p1;\n\t.reg .b64 v1, v2, v3, v4, v5, v6, v7;\n\t.reg .b32 a1, a2, a3, a4, a5, a6, a7;\n\t"
-      "setp.ne.b32 p0, %4, 0;\n\tsetp.eq.b32 p1, 0, 0;\n\t"
-      "add.s64 v1, %2, 128;\n\tadd.s64 v2, %2, 256;\n\tadd.s64 v3, %2, 384;\n\tadd.s64 v4, %2, 512;\n\t"
-      "add.s64 v5, %2, 640;\n\tadd.s64 v6, %2, 768;\n\tadd.s64 v7, %2, 896;\n\t"
-      "add.s32 a1, %1, 8;\n\tadd.s32 a2, %1, 16;\n\tadd.s32 a3, %1, 24;\n\tadd.s32 a4, %1, 32;\n\t"
-      "add.s32 a5, %1, 40;\n\tadd.s32 a6, %1, 48;\n\tadd.s32 a7, %1, 56;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a1], v1, %3, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a2], v2, %3, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a3], v3, %3, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a4], v4, %3, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a5], v5, %3, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a6], v6, %3, p1;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], [a7], v7, %3, p1;\n\t}\n" ::"r"(tO), "r"(tP), "l"(vd), "r"(idesc), "r"(acc0)
-      : "memory");
+// O[tO] (+)= P[tP] V: KS steps of K = 16 (P advances 8 TMEM columns, V 16 rows = 2048 B = +128 per step); acc0 = 0 starts an item.
+template <int KS>
+__device__ __forceinline__ void mma_pv(uint32_t tO, uint32_t tP, uint64_t vd, uint32_t idesc, uint32_t acc0) {
+  mma_ts(tO, tP, vd, idesc, acc0);
+#pragma unroll
+  for (int k = 1; k < KS; ++k) mma_ts(tO, tP + uint32_t(8 * k), vd + uint64_t(128 * k), idesc, 1u);
 }
 
-// 32 score columns -> 16 packed P words, IN PLACE: P word i (columns 2i, 2i+1) replaces s[i], which pair i/2 has already consumed
-// (saves 16 registers against a separate output array).  la / lb: packed fp32x2 partial row sums; amax: largest |a| seen on the
-// polynomial path.
-template <int DT, int NPOLY>
-__device__ __forceinline__ void att_chain_chunk(uint32_t (&s)[32], u64& la, u64& lb, float& amax, const u64 sc2, const u64 negm2) {
+// W score columns -> W/2 packed P words, IN PLACE: P word i (columns 2i, 2i+1) replaces s[i], which pair i/2 has already consumed
+// (no separate output array).  la / lb: packed fp32x2 partial row sums; amax: largest |a| seen on the polynomial path.
+template <int DT, int NPOLY, int W>
+__device__ __forceinline__ void att_chain_chunk(uint32_t (&s)[W], u64& la, u64& lb, float& amax, const u64 sc2, const u64 negm2) {
   using O16 = Op16<DT>;
 #pragma unroll
-  for (int i = 0; i < 16; ++i) {
+  for (int i = 0; i < W / 2; ++i) {
     const u64 a = f2_fma(f2_pack(s[2 * i], s[2 * i + 1]), sc2, negm2);
     float p0, p1;
+#ifdef ATC_NOEXP      // timing diagnostic: no exponentials at all (results are garbage)
+    if (true) {
+      float a0, a1;
+      f2_unpack(a, a0, a1);
+      p0 = a0 * 1e-3f;
+      p1 = a1 * 1e-3f;
+    } else
+#endif
     if ((i & 7) >= 8 - NPOLY) {
       // 2^a = 2^round(a) * 2^r, r in [-0.5, 0.5]: round through the 1.5 * 2^23 magic add, minimax cubic for 2^r, the integer
-      // part added into the exponent field (LEA).  Valid for |a| <= 126; amax lets the caller flag rows outside that range.
+      // part added into the exponent field.  Valid for |a| <= 126; amax lets the caller flag rows outside that range.
       float a0, a1;
       f2_unpack(a, a0, a1);
       amax = fmaxf(amax, fmaxf(fabsf(a0), fabsf(a1)));
@@ -256,33 +275,38 @@ struct AtcStep {
   }
 };
 
-template <int DT>
-__global__ void __launch_bounds__(ATC_THREADS, 1)
-attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const AttnParams p, const void* qkv_base) {
+template <int DT, typename Cfg>
+__global__ void __launch_bounds__(Cfg::THREADS, 1)
+attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __grid_constant__ CUtensorMap tmap_kv, const AttnParams p,
+                           const void* qkv_base) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using O16 = Op16<DT>;
+  constexpr int NCH = Cfg::NCH, BKV = Cfg::BKV, CW = Cfg::CW, R = Cfg::R;
+  constexpr int KV_BYTES = Cfg::KV_BYTES, SLOT_BYTES = Cfg::SLOT_BYTES;
+  constexpr int SMW = 4 * NCH;              // softmax warps
   uint8_t* sQ = smem;                       // [2]
-  uint8_t* sKV = smem + ATC_OFF_KV;         // [ATC_R] slots of {K tile, V tile}: slot of "virtual tile" vg holds K(vg) and V(vg - 3)
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATC_OFF_BAR);
-  uint64_t* q_full = bars;                  // [2]  Q tile of item n landed
-  uint64_t* q_empty = q_full + 2;           // [2]  last QK^T of the item retired
-  uint64_t* kv_full = q_empty + 2;          // [R]  K(vg) and V(vg-3) landed
-  uint64_t* kv_empty = kv_full + ATC_R;     // [R]  QK^T(vg) and PV(vg-3) retired
-  uint64_t* s_full = kv_empty + ATC_R;      // [3]  scores of the chain's current tile are in TMEM
-  uint64_t* p_full = s_full + 3;            // [3]  P written in place (4 warp arrivals)
-  uint64_t* o_full = p_full + 3;            // [2]  last PV of the item retired
-  uint64_t* o_empty = o_full + 2;           // [2]  epilogue has O, m_ref and the l partials of the item in registers (4 arrivals)
-  uint64_t* mref_full = o_empty + 2;        // [2]  m_ref of the item published (4 arrivals)
-  uint64_t* lpart_full = mref_full + 2;     // [2]  every chain has published its partial row sums of the item (12 arrivals)
+  uint8_t* sKV = smem + Cfg::OFF_KV;        // [R] slots of {K tile, V tile}: the slot of "virtual tile" vg holds K(vg) and V(vg - NCH)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
+  uint64_t* q_full = bars;                  // [2]    Q tile of item n landed
+  uint64_t* q_empty = q_full + 2;           // [2]    last QK^T of the item retired
+  uint64_t* kv_full = q_empty + 2;          // [R]    K(vg) and V(vg - NCH) landed
+  uint64_t* kv_empty = kv_full + R;         // [R]    QK^T(vg) and PV(vg - NCH) retired (two arrivals: one per issuing warp)
+  uint64_t* s_full = kv_empty + R;          // [NCH]  scores of the chain's current tile are in TMEM
+  uint64_t* p_full = s_full + NCH;          // [NCH]  P written in place (4 warp arrivals)
+  uint64_t* pv_done = p_full + NCH;         // [NCH]  PV of the chain's tile retired: its buffer may take the next scores
+  uint64_t* o_full = pv_done + NCH;         // [2]    last PV of the item retired
+  uint64_t* o_empty = o_full + 2;           // [2]    epilogue has O, m_ref and the l partials of the item in registers (4 arrivals)
+  uint64_t* mref_full = o_empty + 2;        // [2]    m_ref of the item published (4 arrivals)
+  uint64_t* lpart_full = mref_full + 2;     // [2]    the row sums of all tiles of the item are in shared memory (one arrival: PV issuer)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lpart_full + 2);
-  float* s_mref = reinterpret_cast<float*>(smem + ATC_OFF_MREF);     // [2][128]
-  float* s_lpart = reinterpret_cast<float*>(smem + ATC_OFF_LPART);   // [2][3][128]
+  float* s_mref = reinterpret_cast<float*>(smem + Cfg::OFF_MREF);     // [2][128]
+  float* s_lpart = reinterpret_cast<float*>(smem + Cfg::OFF_LPART);   // [2][NKV_MAX][128]: row sum of tile j of the item
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const int nq = (p.N + ATT_BQ - 1) / ATT_BQ;
-  const int nkv = (p.N + ATT_BKV - 1) / ATT_BKV;
-  const int valid_last = p.N - (nkv - 1) * ATT_BKV;        // 1..128 real keys in the last KV tile
+  const int nkv = (p.N + BKV - 1) / BKV;
+  const int valid_last = p.N - (nkv - 1) * BKV;            // 1..BKV real keys in the last KV tile
   const int nc_last = (valid_last + 31) & ~31;             // score columns computed for it
   const int n_items = p.B * p.H * nq;
   const int n_local = (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
@@ -299,126 +323,80 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       mbar_init(&o_full[i], 1);
       mbar_init(&o_empty[i], 4);
       mbar_init(&mref_full[i], 4);
-      mbar_init(&lpart_full[i], 12);
+      mbar_init(&lpart_full[i], 1);
     }
-    for (int i = 0; i < ATC_R; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-    for (int i = 0; i < 3; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); }
+    for (int i = 0; i < R; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
+    for (int i = 0; i < NCH; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
   }
-  if (warp == 13) {
-    if (lane == 0) tma_prefetch_desc(&tmap_qkv);
+  if (warp == SMW + 1) {
+    if (lane == 0) { tma_prefetch_desc(&tmap_q); tma_prefetch_desc(&tmap_kv); }
     tmem_alloc<512>(tmem_slot);
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  // TMEM columns: [0,384) three score / P buffers, [384,512) two O accumulators
+  // TMEM columns: [0, NCH * BKV) score / P buffers, [384, 512) two O accumulators
 
-  if (warp >= 12) {
-  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATC_REGS_AUX));
-  if (warp == 12) {
-    // ------------------------------------------------------------------ TMA producer (one lane)
-    // Loads go out in the order the tensor pipe consumes them: K(0..2), then {V(g), K(g+3)} for g = 0, 1, ...; the pair shares a
-    // ring slot and one mbarrier, so the issuer waits once per tile.
-    if (lane == 0) {
-      unsigned d_kw = 0, d_qw = 0;
-      const long long d_start = clock64();
-      (void)d_start;
-      // K stream state: item of the next K tile and its coordinates (recomputed once per ITEM: no per-tile divisions)
-      int kn = 0, kj = 0, k_row0 = 0, k_col = 0;
-      auto k_item = [&]() {
-        const int it = int(blockIdx.x) + kn * int(gridDim.x);
-        const int qt = it % nq, bh = it / nq, h = bh % p.H, b = bh / p.H;
-        k_row0 = b * p.N;
-        k_col = h * ATT_D;
-        ATC_T0();
-        mbar_wait(&q_empty[kn & 1], ((kn >> 1) & 1) ^ 1);
-        ATC_ACC(d_qw);
-        mbar_expect_tx(&q_full[kn & 1], ATT_TILE_BYTES);
-        tma_load_2d(sQ + (kn & 1) * ATT_TILE_BYTES, &tmap_qkv, &q_full[kn & 1], k_col, k_row0 + qt * ATT_BQ);
-      };
-      int vn = 0, vj = 0, v_row0 = 0, v_col = 0;      // V stream
-      auto v_item = [&]() {
-        const int it = int(blockIdx.x) + vn * int(gridDim.x);
-        const int bh = it / nq, h = bh % p.H, b = bh / p.H;
-        v_row0 = b * p.N;
-        v_col = 2 * p.H * ATT_D + h * ATT_D;
-      };
-      int slot = 0;
-      uint32_t phase = 0;
-#pragma unroll 1
-      for (int vg = 0; vg < n_tiles + 3; ++vg) {
-        const bool has_k = vg < n_tiles, has_v = vg >= 3;
-        ATC_T0();
-        mbar_wait(&kv_empty[slot], phase ^ 1);
-        ATC_ACC(d_kw);
-        mbar_expect_tx(&kv_full[slot], (has_k ? ATT_TILE_BYTES : 0) + (has_v ? ATT_TILE_BYTES : 0));
-        uint8_t* dst = sKV + slot * (2 * ATT_TILE_BYTES);
-        if (has_v) {
-          if (vj == 0) v_item();
-          tma_load_2d(dst + ATT_TILE_BYTES, &tmap_qkv, &kv_full[slot], v_col, v_row0 + vj * ATT_BKV);
-          if (++vj == nkv) { vj = 0; ++vn; }
-        }
-        if (has_k) {
-          if (kj == 0) k_item();
-          tma_load_2d(dst, &tmap_qkv, &kv_full[slot], p.H * ATT_D + k_col, k_row0 + kj * ATT_BKV);
-          if (++kj == nkv) { kj = 0; ++kn; }
-        }
-        if (++slot == ATC_R) { slot = 0; phase ^= 1; }
-      }
-#ifdef ATC_DIAG
-      if (p.lse != nullptr) {
-        float* d = p.lse + size_t(blockIdx.x) * 256 + 200;
-        d[0] = float(d_kw); d[1] = 0.f; d[2] = float(d_qw); d[3] = float(clock64() - d_start);
-      }
-#endif
-    }
-  } else if (warp == 13) {
-    // ------------------------------------------------------------------ MMA issuer
-    // The WHOLE warp runs this loop (uniform control flow: addresses, descriptors and counters stay in uniform registers, no
-    // per-instruction R2UR); one elected lane issues the tcgen05 instructions.  Per tile g: wait P(g) and slot {V(g), K(g+3)},
-    // issue PV(g) and QK^T(g+3), commit.
-    constexpr uint32_t idesc_qk = make_idesc(DT, 128, 128, 0, 0);
-    const uint32_t idesc_qk_last = make_idesc(DT, 128, nc_last, 0, 0);
-    constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);  // B = V, MN-major
-    const uint64_t qdesc0 = make_sdesc(smem_u32(sQ), 16, 1024);
-    const uint64_t kdesc0 = make_sdesc(smem_u32(sKV), 16, 1024);
-    const uint64_t vdesc0 = make_sdesc(smem_u32(sKV + ATT_TILE_BYTES), 8192, 1024);
-    unsigned d_q = 0, d_o = 0, d_p = 0, d_kv = 0;
+  if (warp >= SMW) {
+  asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_AUX));
+  if (warp == SMW) {
+    // ------------------------------------------------------------------ TMA producer
+    // Loads go out in the order the tensor pipe consumes them: K(0..NCH-1), then {V(g), K(g+NCH)} for g = 0, 1, ...; the pair
+    // shares a ring slot and one mbarrier.  The whole warp runs the loop (uniform control flow), one elected lane issues.
+    unsigned d_kw = 0, d_qw = 0;
     const long long d_start = clock64();
     (void)d_start;
-    int qn = 0, qj = 0, qc = 0;        // next QK^T: item, tile in item, chain
-    // QK^T of the next tile from the K half of `slot` into chain qc's buffer; caller has waited for the slot
-    auto issue_qk = [&](const int slot) {
-      const uint64_t qd = qdesc0 + uint64_t((qn & 1) * (ATT_TILE_BYTES >> 4));
-      const uint64_t kd = kdesc0 + uint64_t(slot * (2 * ATT_TILE_BYTES >> 4));
-      const uint32_t tS = tmem_base + uint32_t(qc) * 128u;
-      const bool last = (qj == nkv - 1);
-      const uint32_t idesc = last ? idesc_qk_last : idesc_qk;
-      if (elect_one()) {
-        mma_qk4(tS, qd, kd, idesc);
-        tc_commit(&s_full[qc]);
-        if (last) tc_commit(&q_empty[qn & 1]);
-      }
-      __syncwarp();
-      if (++qc == 3) qc = 0;
-      if (++qj == nkv) { qj = 0; ++qn; }
-    };
+    AtcStep step;
+    step.init(int(gridDim.x), nq, p.H);
+    AtcItem kit = step.first(int(blockIdx.x)), vit = kit;      // items of the next K tile / next V tile
+    int kn = 0, kj = 0, vj = 0;
     int slot = 0;
     uint32_t phase = 0;
-    auto next_slot = [&]() { if (++slot == ATC_R) { slot = 0; phase ^= 1; } };
-    // prologue: QK^T(0..2) (their slots hold a K tile only)
-    for (int vg = 0; vg < 3 && vg < n_tiles; ++vg) {
-      if (qj == 0) mbar_wait(&q_full[qn & 1], (qn >> 1) & 1);
-      mbar_wait(&kv_full[slot], phase);
-      tc_fence_after();
-      issue_qk(slot);
-      if (elect_one()) tc_commit(&kv_empty[slot]);
+#pragma unroll 1
+    for (int vg = 0; vg < n_tiles + NCH; ++vg) {
+      const bool has_k = vg < n_tiles, has_v = vg >= NCH;
+      ATC_T0();
+      if (has_k && kj == 0) mbar_wait(&q_empty[kn & 1], ((kn >> 1) & 1) ^ 1);
+      ATC_ACC(d_qw);
+      mbar_wait(&kv_empty[slot], phase ^ 1);
+      ATC_ACC(d_kw);
+      if (elect_one()) {
+        uint8_t* dst = sKV + slot * SLOT_BYTES;
+        mbar_expect_tx(&kv_full[slot], (has_k ? KV_BYTES : 0) + (has_v ? KV_BYTES : 0));
+        if (has_v) tma_load_2d(dst + KV_BYTES, &tmap_kv, &kv_full[slot], (2 * p.H + vit.h) * ATT_D, vit.b * p.N + vj * BKV);
+        if (has_k) {
+          if (kj == 0) {
+            mbar_expect_tx(&q_full[kn & 1], ATT_TILE_BYTES);
+            tma_load_2d(sQ + (kn & 1) * ATT_TILE_BYTES, &tmap_q, &q_full[kn & 1], kit.h * ATT_D, kit.b * p.N + kit.qt * ATT_BQ);
+          }
+          tma_load_2d(dst, &tmap_kv, &kv_full[slot], (p.H + kit.h) * ATT_D, kit.b * p.N + kj * BKV);
+        }
+      }
       __syncwarp();
-      next_slot();
+      if (has_v && ++vj == nkv) { vj = 0; step.next(vit); }
+      if (has_k && ++kj == nkv) { kj = 0; ++kn; step.next(kit); }
+      if (++slot == R) { slot = 0; phase ^= 1; }
     }
-    if (n_tiles < 3) { for (int vg = n_tiles; vg < 3; ++vg) next_slot(); }   // (unreachable: n_tiles >= 2 * n_local and nkv >= 2 ... kept for safety)
+#ifdef ATC_DIAG
+    if (p.lse != nullptr && lane == 0) {
+      float* d = p.lse + size_t(blockIdx.x) * 512 + 400;
+      d[0] = float(d_kw); d[1] = 0.f; d[2] = float(d_qw); d[3] = float(clock64() - d_start);
+    }
+#endif
+  } else if (warp == SMW + 1) {
+    // ------------------------------------------------------------------ PV issuer: O(item) += P(g) V(g)
+    // Two issuing warps (this one and the QK^T issuer below) share the tensor pipe's queue: tcgen05.mma issue blocks while the
+    // queue is full, and with one issuer the per-tile bookkeeping (barrier tests, descriptors, commits: ~600 cycles of a single
+    // latency-bound thread) ran with the pipe idle.  Cross-warp order is by COMPLETION: QK^T(g+NCH) waits for pv_done of PV(g).
+    constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);  // B = V, MN-major
+    const uint64_t vdesc0 = make_sdesc(smem_u32(sKV + KV_BYTES), 8192, 1024);
+    unsigned d_o = 0, d_p = 0, d_kv = 0, d_pv = 0, d_cm = 0;
+    const long long d_start = clock64();
+    (void)d_start;
+    int slot = NCH % R;
+    uint32_t phase = (NCH / R) & 1;
     int n = 0, j = 0, c = 0;
     uint32_t pbits = 0;                // per-chain phase parity of p_full
 #pragma unroll 1
@@ -426,78 +404,112 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
       ATC_T0();
       if (j == 0) mbar_wait(&o_empty[n & 1], ((n >> 1) & 1) ^ 1);     // epilogue of item n-2 has drained this accumulator
       ATC_ACC(d_o);
-      const bool more_qk = g + 3 < n_tiles;
-      if (more_qk && qj == 0) mbar_wait(&q_full[qn & 1], (qn >> 1) & 1);
-      ATC_ACC(d_q);
-      mbar_wait(&p_full[c], (pbits >> c) & 1u);
-      pbits ^= 1u << c;
+      // the two per-tile barriers are tested together (a try_wait costs ~90 cycles even when the phase is long complete)
+      const uint32_t ppar = (pbits >> c) & 1u;
+      const bool ok_p = mbar_try_wait(&p_full[c], ppar), ok_kv = mbar_try_wait(&kv_full[slot], phase);
+      if (!ok_p) mbar_wait(&p_full[c], ppar);
       ATC_ACC(d_p);
-      mbar_wait(&kv_full[slot], phase);
+      if (!ok_kv) mbar_wait(&kv_full[slot], phase);
       ATC_ACC(d_kv);
+      pbits ^= 1u << c;
+      // Every softmax warp stores its tile's row sums BEFORE it arrives on p_full, and this warp has now acquired the p_full of
+      // every tile of the item: one release-arrive here hands all of them to the epilogue (no per-chain flush protocol).
+      if (j == nkv - 1 && lane == 0) mbar_arrive(&lpart_full[n & 1]);
       tc_fence_after();
-      const uint32_t tP = tmem_base + uint32_t(c) * 128u;
+      const uint32_t tP = tmem_base + uint32_t(c * BKV);
       const uint32_t tO = tmem_base + 384u + uint32_t(n & 1) * 64u;
-      const uint64_t vd = vdesc0 + uint64_t(slot * (2 * ATT_TILE_BYTES >> 4));
+      const uint64_t vd = vdesc0 + uint64_t(slot * (SLOT_BYTES >> 4));
       const bool last = (j == nkv - 1);
       if (elect_one()) {
         if (!last) {
-          mma_pv8(tO, tP, vd, idesc_pv, uint32_t(j));
+          mma_pv<BKV / 16>(tO, tP, vd, idesc_pv, uint32_t(j));
         } else {
           const int ksteps = nc_last >> 4;
 #pragma unroll 1
           for (int k = 0; k < ksteps; ++k) mma_ts(tO, tP + uint32_t(8 * k), vd + uint64_t(k * 128), idesc_pv, (j | k) ? 1u : 0u);
           tc_commit(&o_full[n & 1]);
         }
+        tc_commit(&pv_done[c]);
+        tc_commit(&kv_empty[slot]);
+        if (g + NCH >= n_tiles) tc_commit(&kv_empty[slot]);     // no QK^T(g+NCH): this warp supplies the slot's second arrival too
       }
       __syncwarp();
-      if (more_qk) issue_qk(slot);      // QK^T(g+3) overwrites this chain's buffer; the tensor pipe executes in issue order
-      if (elect_one()) tc_commit(&kv_empty[slot]);
-      __syncwarp();
-      next_slot();
-      if (++c == 3) c = 0;
+      ATC_ACC(d_pv);
+      if (++slot == R) { slot = 0; phase ^= 1; }
+      if (++c == NCH) c = 0;
       if (++j == nkv) { j = 0; ++n; }
+      ATC_ACC(d_cm);
     }
 #ifdef ATC_DIAG
     if (p.lse != nullptr && lane == 0) {
-      float* d = p.lse + size_t(blockIdx.x) * 256 + 208;
-      d[0] = float(d_q); d[1] = float(d_kv); d[2] = float(d_o); d[3] = float(d_p); d[4] = 0.f; d[5] = float(clock64() - d_start);
+      float* d = p.lse + size_t(blockIdx.x) * 512 + 408;
+      d[0] = 0.f; d[1] = float(d_kv); d[2] = float(d_o); d[3] = float(d_p); d[4] = 0.f; d[5] = float(clock64() - d_start); d[6] = float(d_pv); d[7] = 0.f; d[8] = float(d_cm);
+    }
+#endif
+  } else if (warp == SMW + 2) {
+    // ------------------------------------------------------------------ QK^T issuer: S(chain) = Q(item) K(vg)^T
+    constexpr uint32_t idesc_qk = make_idesc(DT, 128, BKV, 0, 0);
+    const uint32_t idesc_qk_last = make_idesc(DT, 128, nc_last, 0, 0);
+    const uint64_t qdesc0 = make_sdesc(smem_u32(sQ), 16, 1024);
+    const uint64_t kdesc0 = make_sdesc(smem_u32(sKV), 16, 1024);
+    unsigned d_q = 0, d_kv = 0, d_pvd = 0, d_qk = 0;
+    const long long d_start = clock64();
+    (void)d_start;
+    int slot = 0;
+    uint32_t phase = 0;
+    int qn = 0, qj = 0, qc = 0;        // item, tile in item, chain of the tile
+    uint32_t dbits = 0;                // per-chain phase parity of pv_done
+#pragma unroll 1
+    for (int vg = 0; vg < n_tiles; ++vg) {
+      ATC_T0();
+      if (qj == 0) mbar_wait(&q_full[qn & 1], (qn >> 1) & 1);
+      ATC_ACC(d_q);
+      const uint32_t dpar = (dbits >> qc) & 1u;
+      const bool need_pv = vg >= NCH;                                 // the chain's buffer still holds P(vg - NCH) until PV(vg - NCH) retires
+      const bool ok_d = need_pv ? mbar_try_wait(&pv_done[qc], dpar) : true, ok_kv = mbar_try_wait(&kv_full[slot], phase);
+      if (!ok_d) mbar_wait(&pv_done[qc], dpar);
+      ATC_ACC(d_pvd);
+      if (!ok_kv) mbar_wait(&kv_full[slot], phase);
+      ATC_ACC(d_kv);
+      if (need_pv) dbits ^= 1u << qc;
+      tc_fence_after();
+      const uint64_t qd = qdesc0 + uint64_t((qn & 1) * (ATT_TILE_BYTES >> 4));
+      const uint64_t kd = kdesc0 + uint64_t(slot * (SLOT_BYTES >> 4));
+      const uint32_t tS = tmem_base + uint32_t(qc * BKV);
+      const bool last = (qj == nkv - 1);
+      if (elect_one()) {
+        mma_qk4(tS, qd, kd, last ? idesc_qk_last : idesc_qk);
+        tc_commit(&s_full[qc]);
+        tc_commit(&kv_empty[slot]);
+        if (vg < NCH) tc_commit(&kv_empty[slot]);                     // K-only slot of the prologue: no PV uses it
+        if (last) tc_commit(&q_empty[qn & 1]);
+      }
+      __syncwarp();
+      ATC_ACC(d_qk);
+      if (++slot == R) { slot = 0; phase ^= 1; }
+      if (++qc == NCH) qc = 0;
+      if (++qj == nkv) { qj = 0; ++qn; }
+    }
+#ifdef ATC_DIAG
+    if (p.lse != nullptr && lane == 0) {
+      float* d = p.lse + size_t(blockIdx.x) * 512 + 420;
+      d[0] = float(d_q); d[1] = float(d_kv); d[2] = float(d_pvd); d[3] = float(d_qk); d[4] = float(clock64() - d_start);
     }
 #endif
   }
   } else {
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATC_REGS_SOFTMAX));
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_SM));
     // ------------------------------------------------------------------ softmax chains: thread <-> query row (TMEM lane)
     const int c = warp >> 2;
     const int row = (warp & 3) * 32 + lane;
-    const uint32_t tS = tmem_base + uint32_t(c) * 128u + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t tS = tmem_base + uint32_t(c * BKV) + (uint32_t((warp & 3) * 32) << 16);
     const float sc = p.scale_log2;
     const u64 sc2 = f2_packf(sc, sc);
-    int cur_n = -1, flushed = 0;
-    unsigned d_s = 0, d_mref = 0, d_flush = 0, d_epi = 0, d_exp = 0, d_lead = 0, d_e1 = 0, d_e2 = 0, d_f1 = 0, d_bad = 0, d_e3 = 0, d_e4 = 0, d_e0 = 0;
+    int cur_n = -1;
+    unsigned d_s = 0, d_mref = 0, d_flush = 0, d_epi = 0, d_exp = 0, d_lead = 0;
     const long long d_start = clock64();
-    u64 la = 0ull, lb = 0ull;
-    float amax = 0.f;
+    (void)d_start;
     float m_ref = 0.f;
-    auto flush_to = [&](int upto) {       // publish this chain's partial row sums of items [flushed, upto)
-      while (flushed < upto) {
-        const int m = flushed;
-        float lt = 0.f;
-        if (m == cur_n) {
-          float x0, x1, y0, y1;
-          f2_unpack(la, x0, x1);
-          f2_unpack(lb, y0, y1);
-          lt = (x0 + x1) + (y0 + y1);
-          if (amax > 126.0f) lt = INFINITY;          // a polynomial-path exponent left its valid range: force the exact redo
-        }
-        ATC_T0();
-        mbar_wait(&o_empty[m & 1], ((m >> 1) & 1) ^ 1);                // the epilogue of item m-2 has read its slots
-        ATC_ACC(d_f1);
-        s_lpart[(m & 1) * 384 + c * 128 + row] = lt;
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&lpart_full[m & 1]);
-        ++flushed;
-      }
-    };
     AtcStep step;
     step.init(int(gridDim.x), nq, p.H);
     AtcItem cur_it = step.first(int(blockIdx.x)), prev_it = cur_it;   // coordinates of items cur_n (0 before the first tile) / cur_n - 1
@@ -506,159 +518,162 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
     // their first output word and are recomputed exactly after the main loop (keeps the function call and its register
     // traffic out of the pipelined part of the kernel).
     auto epilogue = [&](const int n, const AtcItem x) {
-      ATC_T0();
       const int par = n & 1;
       const uint32_t ph = (n >> 1) & 1;
-      ATC_ACC(d_e0);
       mbar_wait(&lpart_full[par], ph);
-      ATC_ACC(d_e1);
-      const float l = s_lpart[par * 384 + row] + s_lpart[par * 384 + 128 + row] + s_lpart[par * 384 + 256 + row];
+      // the tiles' row sums are added in tile order, whichever chain produced them: the result does not depend on how this
+      // CTA's items happened to line up with the chains (a clip computed alone or inside a batch gives identical bits)
+      float l = 0.f;
+      for (int k = 0; k < nkv; ++k) l += s_lpart[(par * Cfg::NKV_MAX + k) * 128 + row];
       const float mr = s_mref[par * 128 + row];
       mbar_wait(&o_full[par], ph);
-      ATC_ACC(d_e2);
       tc_fence_after();
       const uint32_t tO = tmem_base + 384u + uint32_t(par) * 64u + (uint32_t((warp & 3) * 32) << 16);
       const int qrow = x.qt * ATT_BQ + row;
       const float inv_l = 1.0f / l;
       bool good = (l > 0.f) && (l < INFINITY);
       typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.out) + size_t(x.b * p.N + qrow) * p.ld_out + x.h * ATT_D;
-      uint32_t v[32], w[32];
-      tmem_ld32(tO, v);
-      tmem_ld32(tO + 32u, w);
-      tc_wait_ld();
-      reg_fence32(v);
-      reg_fence32(w);
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_empty[par]);       // O, m_ref and the l partials of this slot are in registers
-      ATC_ACC(d_e3);
-      // one column suffices for the finiteness test: an inf / NaN in a row of P reaches all 64 columns of that row of O
-      good = good && (fabsf(__uint_as_float(v[0]) * inv_l) < INFINITY);
-      if (qrow < p.N) {
-        if (!good) {
-          ++n_bad;                // the first output word of the row becomes the NaN sentinel 0x7fff7fff (both 16-bit halves)
+      if (qrow < p.N && p.lse != nullptr) p.lse[(size_t(x.b) * p.H + x.h) * p.N + qrow] = mr + log2f(l);
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(tO + uint32_t(half * 32), v);
+        tc_wait_ld();
+        if (half == 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&o_empty[par]);       // O, m_ref and the l partials of this slot are in registers
         }
-        if (p.lse != nullptr) p.lse[(size_t(x.b) * p.H + x.h) * p.N + qrow] = mr + log2f(l);
+        // one column suffices for the finiteness test: an inf / NaN in a row of P reaches all 64 columns of that row of O
+        if (half == 0) {
+          good = good && (fabsf(__uint_as_float(v[0]) * inv_l) < INFINITY);
+          if (!good && qrow < p.N) ++n_bad;   // the first output word of the row becomes the NaN sentinel 0x7fff7fff
+        }
+        if (qrow < p.N) {
 #pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          st_global_v4(dst + i, (i == 0 && !good) ? 0x7fff7fffu : O16::pack(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
-                       O16::pack(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
-                       O16::pack(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
-                       O16::pack(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
-#pragma unroll
-        for (int i = 0; i < 32; i += 8)
-          st_global_v4(dst + 32 + i, O16::pack(__uint_as_float(w[i]) * inv_l, __uint_as_float(w[i + 1]) * inv_l),
-                       O16::pack(__uint_as_float(w[i + 2]) * inv_l, __uint_as_float(w[i + 3]) * inv_l),
-                       O16::pack(__uint_as_float(w[i + 4]) * inv_l, __uint_as_float(w[i + 5]) * inv_l),
-                       O16::pack(__uint_as_float(w[i + 6]) * inv_l, __uint_as_float(w[i + 7]) * inv_l));
+          for (int i = 0; i < 32; i += 8)
+            st_global_v4(dst + half * 32 + i,
+                         (half == 0 && i == 0 && !good) ? 0x7fff7fffu : O16::pack(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
+                         O16::pack(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
+                         O16::pack(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
+                         O16::pack(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
+        }
       }
-      ATC_ACC(d_e4);
     };
     // Masked keys (past the end of the clip, last KV tile only) get the score that maps to a = -120: p = 2^-120 is zero for
     // every purpose (0 in fp16, 7.5e-37 in bf16 against row sums >= 1) and stays inside the polynomial path's valid range.
     const float inv_sc = 1.0f / sc;
     int n = 0, j = c;
     while (j >= nkv) { j -= nkv; ++n; }
-    // three "virtual" tiles past the end give every chain one more pass through the item-change / epilogue logic below, so the
-    // flush and the epilogue have exactly one call site each (code size: the whole kernel has to live in the instruction cache)
+    // NCH "virtual" tiles past the end give every chain one more pass through the item-change / epilogue logic below, so the
+    // flush and the epilogue have exactly one call site each.
 #pragma unroll 1
-    for (int g = c; g < n_tiles + 3; g += 3) {
+    for (int g = c; g < n_tiles + NCH; g += NCH) {
       bool new_item = false;
       ATC_T0();
       if (n != cur_n) {
-        flush_to(n < n_local ? n : n_local);
         int k = cur_n < 0 ? 0 : cur_n;
         while (k < n) { prev_it = cur_it; step.next(cur_it); ++k; }    // cur_it = item n, prev_it = item n - 1
         cur_n = n;
-        la = 0ull; lb = 0ull; amax = 0.f;
         new_item = true;
+        // the row-sum and m_ref slots of this parity were last read by the epilogue of item n - 2
+        if (n < n_local) mbar_wait(&o_empty[n & 1], ((n >> 1) & 1) ^ 1);
       }
       ATC_ACC(d_flush);
       if (g < n_tiles) {
         const bool last = (j == nkv - 1);
-        const int nch = (last ? nc_last : ATT_BKV) >> 5;
-        const int valid = last ? valid_last : ATT_BKV;
-        mbar_wait(&s_full[c], ((g - c) / 3) & 1);
+        const int ncols = last ? nc_last : BKV;
+        const int valid = last ? valid_last : BKV;
+        mbar_wait(&s_full[c], ((g - c) / NCH) & 1);
         ATC_ACC(d_s);
         tc_fence_after();
-        uint32_t sa[32], sb[32];
+        AtcChunk<CW> ca, cb;
+        u64 la = 0ull, lb = 0ull;      // packed fp32x2 partial row sums of this tile
+        float amax = 0.f;
         if (j == 0) {
           // this chain owns the item's first tile (never the ragged last one: nkv >= 2): exact row max -> the item's reference
           float mx = -INFINITY;
 #pragma unroll 1
-          for (int ch = 0; ch < 4; ++ch) {
-            tmem_ld32(tS + uint32_t(ch * 32), sa);
+          for (int col = 0; col < BKV; col += CW) {
+            ca.ld(tS + uint32_t(col));
             tc_wait_ld();
-            reg_fence32(sa);
+            ca.fence();
             float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-            for (int i = 0; i < 32; i += 2) {
-              m0 = fmaxf(m0, __uint_as_float(sa[i]));
-              m1 = fmaxf(m1, __uint_as_float(sa[i + 1]));
+            for (int i = 0; i < CW; i += 2) {
+              m0 = fmaxf(m0, __uint_as_float(ca.r[i]));
+              m1 = fmaxf(m1, __uint_as_float(ca.r[i + 1]));
             }
             mx = fmaxf(mx, fmaxf(m0, m1));
           }
           m_ref = mx * sc;
-          mbar_wait(&o_empty[n & 1], ((n >> 1) & 1) ^ 1);                // readers of the slot's previous item are done
           s_mref[(n & 1) * 128 + row] = m_ref;
           __syncwarp();
           if (lane == 0) mbar_arrive(&mref_full[n & 1]);
           ATC_ACC(d_lead);
         } else if (new_item) {
-          // first tile of this chain in the item (tiles 1 or 2): pick the reference up
+          // first tile of this chain in the item: pick the reference up
           mbar_wait(&mref_full[n & 1], (n >> 1) & 1);
           m_ref = s_mref[(n & 1) * 128 + row];
           ATC_ACC(d_mref);
         }
         const u64 negm2 = f2_packf(-m_ref, -m_ref);
-        if (last && valid < (nch << 5)) {
+        if (last && valid < ncols) {
           // ragged last tile: overwrite the score columns of keys past the end of the clip (in TMEM, one column per store)
           const uint32_t s_mask = __float_as_uint((m_ref - 120.0f) * inv_sc);
 #pragma unroll 1
-          for (int col = valid; col < (nch << 5); ++col) tmem_st1(tS + uint32_t(col), s_mask);
+          for (int col = valid; col < ncols; ++col) tmem_st1(tS + uint32_t(col), s_mask);
           tc_wait_st();
         }
-        // chunks of 32 columns, two per iteration (registers ping-pong: the next chunk's tcgen05.ld is in flight while this one
+        // chunks of CW columns, two per iteration (registers ping-pong: the next chunk's tcgen05.ld is in flight while this one
         // is exponentiated); P is stored over score columns that have already been consumed
-        tmem_ld32(tS, sa);
+        ca.ld(tS);
         tc_wait_ld();
-        reg_fence32(sa);
+        ca.fence();
 #pragma unroll 1
-        for (int ch = 0; ch < nch; ch += 2) {
-          const bool has_b = ch + 1 < nch, has_a2 = ch + 2 < nch;
-          if (has_b) tmem_ld32(tS + uint32_t((ch + 1) * 32), sb);
-          att_chain_chunk<DT, ATT_CHAIN_NPOLY>(sa, la, lb, amax, sc2, negm2);
-          tmem_st16_lo(tS + uint32_t(ch * 16), sa);
+        for (int col = 0; col < ncols; col += 2 * CW) {
+          const bool has_b = col + CW < ncols, has_a2 = col + 2 * CW < ncols;
+          if (has_b) cb.ld(tS + uint32_t(col + CW));
+          att_chain_chunk<DT, ATT_CHAIN_NPOLY, CW>(ca.r, la, lb, amax, sc2, negm2);
+          ca.st_lo(tS + uint32_t(col >> 1));
           if (has_b) {
             tc_wait_ld();
-            reg_fence32(sb);
-            if (has_a2) tmem_ld32(tS + uint32_t((ch + 2) * 32), sa);
-            att_chain_chunk<DT, ATT_CHAIN_NPOLY>(sb, la, lb, amax, sc2, negm2);
-            tmem_st16_lo(tS + uint32_t((ch + 1) * 16), sb);
+            cb.fence();
+            if (has_a2) ca.ld(tS + uint32_t(col + 2 * CW));
+            att_chain_chunk<DT, ATT_CHAIN_NPOLY, CW>(cb.r, la, lb, amax, sc2, negm2);
+            cb.st_lo(tS + uint32_t((col + CW) >> 1));
             if (has_a2) {
               tc_wait_ld();
-              reg_fence32(sa);
+              ca.fence();
             }
           }
+        }
+        {
+          float x0, x1, y0, y1;
+          f2_unpack(la, x0, x1);
+          f2_unpack(lb, y0, y1);
+          float lt = (x0 + x1) + (y0 + y1);
+          if (amax > 126.0f) lt = INFINITY;          // a polynomial-path exponent left its valid range: force the exact redo
+          s_lpart[((n & 1) * Cfg::NKV_MAX + j) * 128 + row] = lt;
         }
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[c]);
+        if (lane == 0) mbar_arrive(&p_full[c]);          // release: the row sums above and P in TMEM
         ATC_ACC(d_exp);
       }
       // deferred epilogue of the previous item: its last tile was g - 2, i.e. this (real or virtual) tile is tile 1 of item n
-      if (j == 1 && n >= 1) epilogue(n - 1, prev_it);
+      if (j == 1 && n >= 1 && n <= n_local) epilogue(n - 1, prev_it);      // (n > n_local: a virtual tile past the virtual item)
       ATC_ACC(d_epi);
-      j += 3;
+      j += NCH;
       while (j >= nkv) { j -= nkv; ++n; }
     }
     // exact redo of the rows flagged above (none in the common case: one ballot).  Every warp re-walks the items whose epilogue
-    // it ran (tile 1 of item n + 1 belongs to chain (n * nkv + nkv + 1) % 3) and looks for the sentinel in its own rows.
+    // it ran (tile 1 of item m + 1 belongs to chain ((m + 1) * nkv + 1) % NCH) and looks for the sentinel in its own rows.
     if (__any_sync(0xffffffffu, n_bad != 0)) {
       AtcItem x = step.first(int(blockIdx.x));
       for (int m = 0; m < n_local; ++m) {
-        if (((m + 1) * nkv + 1) % 3 == c) {
+        if (((m + 1) * nkv + 1) % NCH == c) {
           const int qrow = x.qt * ATT_BQ + row;
           bool flagged = false;
           if (qrow < p.N) {
@@ -677,16 +692,16 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const A
     }
 #ifdef ATC_DIAG
     if (p.lse != nullptr && lane == 0) {
-      float* d = p.lse + size_t(blockIdx.x) * 256 + warp * 16;
+      float* d = p.lse + size_t(blockIdx.x) * 512 + warp * 16;
       d[0] = float(d_s); d[1] = float(d_mref); d[2] = float(d_flush); d[3] = float(d_epi); d[4] = float(d_exp); d[5] = float(d_lead);
-      d[6] = float(clock64() - d_start); d[7] = float(d_e1); d[8] = float(d_e2); d[9] = float(d_f1); d[10] = float(n_bad); d[11] = float(d_e0); d[12] = float(d_e3); d[13] = float(d_e4);
+      d[6] = float(clock64() - d_start); d[10] = float(n_bad);
     }
 #endif
   }
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 13) {
+  if (warp == SMW + 1) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }

@@ -53,4 +53,16 @@ __global__ void __launch_bounds__(256) adamw_multi_kernel(const AdamWParams a) {
   }
 }
 
+// net_swa <- running average of net (torch.optim.swa_utils semantics: avg += (p - avg) * swa_inv), one launch for all tensors;
+// the epoch-end update of helpers/swa_callback.py / Lightning's StochasticWeightAveraging without a second model copy.
+__global__ void __launch_bounds__(256) swa_fold_multi_kernel(const OptTensor* tensors, const OptChunk* chunks, const float swa_inv) {
+  const OptChunk ch = chunks[blockIdx.x];
+  const OptTensor t = tensors[ch.tensor];
+  const long end = ch.start + OPT_CHUNK < t.n ? ch.start + OPT_CHUNK : t.n;
+  for (long i = ch.start + threadIdx.x; i < end; i += 256) {
+    const float s = t.swa[i];
+    t.swa[i] = s + (t.p[i] - s) * swa_inv;
+  }
+}
+
 }  // namespace mb

@@ -48,7 +48,8 @@ __global__ void __launch_bounds__(1024) bce_logits_kernel(const float* __restric
 
 // ---------------------------------------------------------------------------------------------------------------
 // head backward, part 1: one CTA (256 threads) per clip.  Autograd of models/maest.py:806-810 (final LN, rows 0/1),
-// :906 ((cls+dist)/2) and :909 (head = LayerNorm(eps 1e-5) + Linear), "mean" distillation mode.
+// :906 ((cls+dist)/2) and :909 (head = LayerNorm(eps 1e-5) + Linear), "mean" distillation mode; with `separated` set,
+// :914-925: logits = head(cls), logits_dist = head_dist(dist) (head_dist is a bare Linear), two independent gradients.
 // ---------------------------------------------------------------------------------------------------------------
 struct HeadBwdParams {
   const float* x; int N;                 // [B, N, 768] residual stream after the last block (saved)
@@ -58,16 +59,24 @@ struct HeadBwdParams {
   float* dx;                             // [B, N, 768] gradient stream: rows 0/1 of each clip are WRITTEN here
   float* hz;                             // [B, 768] scratch: head-LN output, consumed by head_wgrad_kernel
   float* d_norm_w; float* d_norm_b; float* d_hln_w; float* d_hln_b;   // accumulated (atomics)
+  int separated;                         // 0: "mean" mode; 1: "separated" (the three fields below are used)
+  const float* dlogits_dist;             // [B, C] gradient of the head_dist logits
+  const float* hdist_w;                  // [C, 768]
+  float* z1out;                          // [B, 768] scratch: final-LN'd dist row, consumed by head_wgrad_kernel for head_dist
 };
 
 __global__ void __launch_bounds__(256) head_bwd_clip_kernel(const HeadBwdParams p) {
   __shared__ float red[8];
   __shared__ float dl[1024];
+  __shared__ float dl2[1024];        // separated mode: d(logits_dist)
   __shared__ float xh[2][D_MODEL];   // normalised (pre-affine) rows 0/1
   __shared__ float rs[2];
   const int b = blockIdx.x, tid = threadIdx.x;
   const float gs = *p.gscale;
-  for (int j = tid; j < p.C; j += 256) dl[j] = p.dlogits[long(b) * p.C + j] * gs;
+  for (int j = tid; j < p.C; j += 256) {
+    dl[j] = p.dlogits[long(b) * p.C + j] * gs;
+    if (p.separated) dl2[j] = p.dlogits_dist[long(b) * p.C + j] * gs;
+  }
   const float* xb = p.x + long(b) * p.N * D_MODEL;
   // recompute the final LN of rows 0/1
   float z[2][3];
@@ -92,19 +101,30 @@ __global__ void __launch_bounds__(256) head_bwd_clip_kernel(const HeadBwdParams 
   // feats, head LN forward (recomputed), d(hz) = dlogits . W
   float f[3], fh[3], s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 3; ++i) { f[i] = 0.5f * (z[0][i] + z[1][i]); s += f[i]; }
+  for (int i = 0; i < 3; ++i) { f[i] = p.separated ? z[0][i] : 0.5f * (z[0][i] + z[1][i]); s += f[i]; }
   const float fmu = block_sum_256(s, red) * (1.0f / D_MODEL);
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < 3; ++i) q += (f[i] - fmu) * (f[i] - fmu);
   const float frstd = rsqrtf(block_sum_256(q, red) * (1.0f / D_MODEL) + 1e-5f);
   float dhz[3] = {0.f, 0.f, 0.f};
+  float dz1[3] = {0.f, 0.f, 0.f};    // separated mode: d loss / d (final-LN'd dist row) = dlogits_dist . W_dist
   __syncthreads();   // dl[] visible
   for (int j = 0; j < p.C; ++j) {
     const float d = dl[j];
     const float* w = p.head_w + long(j) * D_MODEL;
 #pragma unroll
     for (int i = 0; i < 3; ++i) dhz[i] = fmaf(d, __ldg(w + tid + 256 * i), dhz[i]);
+  }
+  if (p.separated) {
+    for (int j = 0; j < p.C; ++j) {
+      const float d = dl2[j];
+      const float* w = p.hdist_w + long(j) * D_MODEL;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) dz1[i] = fmaf(d, __ldg(w + tid + 256 * i), dz1[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < 3; ++i) p.z1out[long(b) * D_MODEL + tid + 256 * i] = z[1][i];
   }
   float g[3], sg = 0.f, sgx = 0.f;
 #pragma unroll
@@ -123,13 +143,13 @@ __global__ void __launch_bounds__(256) head_bwd_clip_kernel(const HeadBwdParams 
   float dfe[3];
 #pragma unroll
   for (int i = 0; i < 3; ++i) dfe[i] = frstd * (g[i] - mg - fh[i] * mgx);   // d loss / d feats
-  // rows 0/1: dy = dfeats / 2 through the final LN
+  // rows 0/1 through the final LN: dy = dfeats / 2 ("mean") or (d cls, d dist) ("separated")
   for (int r = 0; r < 2; ++r) {
     float gg[3], a = 0.f, ax = 0.f;
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int c = tid + 256 * i;
-      const float dy = 0.5f * dfe[i];
+      const float dy = p.separated ? (r == 0 ? dfe[i] : dz1[i]) : 0.5f * dfe[i];
       atomicAdd(p.d_norm_w + c, dy * xh[r][c]);
       atomicAdd(p.d_norm_b + c, dy);
       gg[i] = dy * p.norm_w[c];

@@ -13,8 +13,19 @@ from .maest import _MiniIngredient, get_maest
 
 try:  # pragma: no cover
     import lightning.pytorch as pl
+    from lightning.pytorch.callbacks import Callback as _Callback, ModelCheckpoint
     _LightningModule = pl.LightningModule
+    _HAVE_LIGHTNING = True
 except Exception:  # noqa: BLE001
+    _HAVE_LIGHTNING = False
+
+    class _Callback:            # stand-ins with the constructor surface `configure_callbacks` uses (models/module.py:256-276)
+        pass
+
+    class ModelCheckpoint(_Callback):
+        def __init__(self, monitor=None, mode="min", filename=None, every_n_epochs=None, **kw):
+            self.monitor, self.mode, self.filename, self.every_n_epochs = monitor, mode, filename, every_n_epochs
+
     class _LightningModule(torch.nn.Module):
         def log(self, *a, **k):
             pass
@@ -64,7 +75,9 @@ class Module(_LightningModule):
         self.swa_lrs = swa_lrs
         self.distributed_mode = distributed_mode
         self.optimizer_cfg = dict(MODULE_DEFAULT_CONF["optimizer"], **(optimizer or {}))
-        self.net = net if net is not None else get_maest()      # models/module.py:63 (arguments come from the Sacred ingredient)
+        # models/module.py:63 (arguments come from the Sacred ingredient).  The module trains, so its net defaults to bf16
+        # operands (what the north star names; no loss scaling needed); fp16 operands are opt-in: pass net=get_maest(op_dtype="fp16").
+        self.net = net if net is not None else get_maest(op_dtype="bf16")
         self.validation_outputs = []
         self.test_outputs = []
         self.transformer_block = -1
@@ -181,6 +194,110 @@ class Module(_LightningModule):
         # models/module.py:245-254: {"optimizer": AdamW over all parameters, "lr_scheduler": LambdaLR(epoch lambda)}
         optimizer = self.get_optimizer(self.parameters())
         return {"optimizer": optimizer, "lr_scheduler": self.get_lr_scheduler(optimizer)}
+
+    def configure_callbacks(self):
+        """models/module.py:256-276: best-val-loss checkpoint, per-epoch checkpoint, and (do_swa) the weight-averaging callback
+        that creates `net_swa` on fit start and refreshes it at every epoch end."""
+        callbacks = [ModelCheckpoint(monitor="val_loss", mode="min", filename="{epoch}-{val_loss:.2f}-best"),
+                     ModelCheckpoint(filename="{epoch}", every_n_epochs=1)]
+        if self.do_swa:
+            callbacks.append(StochasticWeightAveragingAndCopy(swa_lrs=self.swa_lrs, swa_epoch_start=self.swa_epoch_start))
+        return callbacks
+
+
+class StochasticWeightAveragingAndCopy(_Callback):
+    """The reference's SWA callback (helpers/swa_callback.py:11-45 on top of Lightning's StochasticWeightAveraging) without
+    the second full-model copy: `net_swa` IS the running average.  From `swa_epoch_start` on, once per epoch (after the last
+    optimiser step of the epoch, which is when Lightning's callback calls `update_parameters`), the fused optimiser folds the
+    current weights into `net_swa` inside its own kernel (`FusedAdamW.step(update_swa=True)`: avg += (p - avg) / (n + 1),
+    torch.optim.swa_utils semantics); before that epoch `net_swa` tracks `net` exactly, as `transfer_weights` of a freshly
+    deep-copied average model does in the reference.  With a non-fused optimiser the same update runs as torch ops.
+
+    Not reproduced (host-side training-loop policy, out of the hot path): the SWA learning-rate annealing (`swa_lrs`,
+    `annealing_epochs`) and the final swap of the averaged weights into `net` at fit end (the reference keeps both nets and
+    validates both, models/module.py:121-146, which is what this callback serves)."""
+
+    def __init__(self, swa_lrs=2e-5, swa_epoch_start=50, **_):
+        self.swa_lrs, self._swa_epoch_start = swa_lrs, swa_epoch_start
+        self.n_averaged = 0
+
+    def on_fit_start(self, trainer, pl_module):
+        import copy
+        max_epochs = getattr(trainer, "max_epochs", None)
+        if isinstance(self._swa_epoch_start, float) and max_epochs:
+            self._swa_epoch_start = int(max_epochs * self._swa_epoch_start)      # helpers/swa_callback.py:31-32
+        if not hasattr(pl_module, "net_swa"):
+            pl_module.net_swa = copy.deepcopy(pl_module.net)                     # helpers/swa_callback.py:43-44
+        for p in pl_module.net_swa.parameters():
+            p.requires_grad_(False)
+
+    @staticmethod
+    def _optimizer(trainer):
+        opts = getattr(trainer, "optimizers", None) or []
+        return opts[0] if opts else None
+
+    def on_train_epoch_start(self, trainer, pl_module):
+        """Arms the fused path: the LAST optimiser step of an averaging epoch also updates net_swa."""
+        self._epoch = int(getattr(trainer, "current_epoch", 0))
+
+    def averaging(self):
+        return getattr(self, "_epoch", 0) >= int(self._swa_epoch_start)
+
+    @torch.no_grad()
+    def on_train_epoch_end(self, trainer, pl_module):
+        from .optim import FusedAdamW
+        if not hasattr(pl_module, "net_swa"):
+            self.on_fit_start(trainer, pl_module)
+        src, dst = list(pl_module.net.parameters()), list(pl_module.net_swa.parameters())
+        if not self.averaging():
+            for d, s_ in zip(dst, src):              # before swa_epoch_start the average model is a copy of the net
+                d.copy_(s_)
+            return
+        opt = self._optimizer(trainer)
+        if isinstance(opt, FusedAdamW) and src and src[0].is_cuda:
+            opt.fold_into_swa(src, dst, self.n_averaged)          # one launch over all tensors
+        else:
+            for d, s_ in zip(dst, src):
+                d.add_((s_ - d) / (self.n_averaged + 1))
+        self.n_averaged += 1
+
+
+class TeacherStudentModule(Module):
+    """models/module.py:279-349: the student has two heads (`distilled_type="separated"`): `head` on the CLS token is trained on
+    the ground truth, `head_dist` on the DIST token on the teacher's soft labels; loss = (BCE + BCE_teacher) / 2."""
+
+    def training_step(self, batch, batch_idx):
+        from .train import training_forward
+        x, f, y, y_teacher = batch
+        mix = None
+        if self.mixup_alpha > 0:
+            mix = my_mixup(len(y), self.mixup_alpha)             # one draw blends x, y and y_teacher (models/module.py:284-295)
+        loss, _, _, loss_standard, loss_teacher = training_forward(self.net, x, (y, y_teacher), mix)
+        self.log_dict({"train_loss": loss, "train_loss_standard": loss_standard, "tran_loss_teacher": loss_teacher},
+                      on_step=True, on_epoch=True, prog_bar=True, logger=True)
+        return loss
+
+    def test_validation_step(self, batch, batch_idx, output_buffer, stage):
+        # models/module.py:317-349.  Like the reference, `logits, _ = net(x)` requires a net whose forward returns two values;
+        # a "separated" net returns three, so the first (CLS) logits are used and the unpacking mismatch of the reference
+        # (ValueError: too many values to unpack) is not reproduced.
+        from . import ops
+        x, f, y, y_teacher = batch
+        outputs = {"y": y.detach(), "y_teacher": y_teacher.detach()}
+        for name, net in self._net_map():
+            with torch.no_grad():
+                logits = net(x)[0]
+            loss_standard, _ = ops.bce_logits(logits, y.to(logits.device))
+            loss_teacher, _ = ops.bce_logits(logits, y_teacher.to(logits.device))
+            loss = (loss_standard + loss_teacher) / 2
+            outputs[self._join((name, "loss_standard"))] = loss_standard
+            outputs[self._join((name, "loss_teacher"))] = loss_teacher
+            outputs[self._join((name, "loss"))] = loss
+            outputs[self._join((name, "y_hat"))] = torch.sigmoid(logits.detach())
+            self.log_dict({self._join((stage, "loss_standard", name)): loss_standard,
+                           self._join((stage, "loss_teacher", name)): loss_teacher, self._join((stage, "loss", name)): loss})
+        output_buffer.append(outputs)
+        return outputs
 
 
 def allreduce_gradients(module: torch.nn.Module, group=None) -> int:

@@ -125,12 +125,13 @@ def mel_ingest(raw: torch.Tensor, frames_read: Optional[torch.Tensor] = None, ro
 
 
 def layernorm16(x: torch.Tensor, w: torch.Tensor, b: torch.Tensor, eps: float, op_dtype=F16,
-                save_stats: bool = False):
+                save_stats: bool = False, out: Optional[torch.Tensor] = None):
     _need_cuda(x, w, b)
     assert x.dtype == torch.float32 and x.shape[-1] == 768 and x.is_contiguous()
     rows = x.numel() // 768
     dt = op_dtype_code(op_dtype)
-    y = torch.empty(x.shape, device=x.device, dtype=_DT2TORCH[dt])
+    y = out if out is not None else torch.empty(x.shape, device=x.device, dtype=_DT2TORCH[dt])
+    assert y.dtype == _DT2TORCH[dt] and y.numel() == x.numel() and y.is_contiguous()
     mean = rstd = None
     if save_stats:
         mean = torch.empty(rows, device=x.device, dtype=torch.float32)
@@ -207,11 +208,15 @@ def ln_finalize(partials: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     return stats
 
 
-def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 0, save_lse: bool = False):
-    """qkv [B*N, 3*heads*64] 16-bit -> o [B*N, heads*64] 16-bit (and, for training, lse fp32 [B, heads, N])."""
+def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 3, save_lse: bool = False,
+              out: Optional[torch.Tensor] = None):
+    """qkv [B*N, 3*heads*64] 16-bit -> o [B*N, heads*64] 16-bit (and, for training, lse fp32 [B, heads, N]).
+    variant 3 (default): chains kernel, 3 x 128 keys (csrc/attention_chain.cuh); 4: 4 x 96 keys; 0 / 1 / 2: the round-1 kernels."""
     _need_cuda(qkv)
     assert qkv.is_contiguous() and qkv.shape == (B * N, 3 * heads * 64)
-    out = torch.empty((B * N, heads * 64), device=qkv.device, dtype=qkv.dtype)
+    if out is None:
+        out = torch.empty((B * N, heads * 64), device=qkv.device, dtype=qkv.dtype)
+    assert out.is_contiguous() and out.shape == (B * N, heads * 64) and out.dtype == qkv.dtype
     lse = torch.empty((B, heads, N), device=qkv.device, dtype=torch.float32) if save_lse else None
     with torch.cuda.device(qkv.device):
         lib = _lib_for(qkv)
@@ -372,7 +377,7 @@ def patch_tokens(mel: torch.Tensor, w_pe16: torch.Tensor, conv_bias, freq_pe, ti
 
 
 def encoder(x: torch.Tensor, B: int, N: int, block_table, n_blocks: int, last_attn_only: bool, op_dtype,
-            attn_variant: int = 0, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+            attn_variant: int = 3, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Run n_blocks transformer blocks in place on the fp32 residual stream x [B*N, 768]."""
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()

@@ -152,3 +152,29 @@ class FusedAdamW(torch.optim.Optimizer):
         if update_swa and self._swa is not None:
             self.n_averaged += 1
         return loss
+
+    @torch.no_grad()
+    def fold_into_swa(self, params, swa_params, n_averaged: int):
+        """swa += (p - swa) / (n_averaged + 1) for every (p, swa) pair in ONE launch (maest_swa_fold): the epoch-end update of
+        the SWA callback (maest_b200.module.StochasticWeightAveragingAndCopy), which makes the averaged model reachable from
+        Lightning without AveragedModel's second copy."""
+        params, swa_params = list(params), list(swa_params)
+        if not params:
+            return
+        dev = params[0].device
+        sig = tuple((p.data_ptr(), s.data_ptr(), p.numel()) for p, s in zip(params, swa_params))
+        cache = getattr(self, "_swa_tables", None)
+        if cache is None or cache[0] != sig:
+            rows, chunks = [], []
+            for ti, (p, s) in enumerate(zip(params, swa_params)):
+                assert p.dtype == s.dtype == torch.float32 and p.is_contiguous() and s.is_contiguous() and p.numel() == s.numel()
+                rows.append(_OptTensor(p.data_ptr(), None, None, None, s.data_ptr(), p.numel()))
+                chunks += [_OptChunk(ti, 0, st) for st in range(0, p.numel(), CHUNK)]
+            tt = torch.frombuffer(bytearray(bytes((_OptTensor * len(rows))(*rows))), dtype=torch.uint8).to(dev)
+            ct = torch.frombuffer(bytearray(bytes((_OptChunk * len(chunks))(*chunks))), dtype=torch.uint8).to(dev)
+            self._swa_tables = cache = (sig, tt, ct, len(chunks))
+        with torch.cuda.device(dev):
+            lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
+            _lib.check(lib.maest_swa_fold(cache[1].data_ptr(), cache[2].data_ptr(), cache[3], 1.0 / (n_averaged + 1),
+                                          torch.cuda.current_stream().cuda_stream), "swa_fold")
+        torch._C._increment_version(swa_params)

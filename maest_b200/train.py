@@ -23,7 +23,11 @@ def _flat_params(model):
 
 
 class MaestTrainStep(torch.autograd.Function):
-    """loss, logits = MaestTrainStep.apply(model, mel, targets, keep_ft, t_offset, *parameters)"""
+    """loss, logits = MaestTrainStep.apply(model, mel, targets, keep_ft, t_offset, *parameters)
+
+    `targets` is one tensor ("mean" mode: BCE(head((cls + dist) / 2), y), models/module.py:88-90) or a pair (y, y_teacher) for
+    distilled_type = "separated" (teacher-student step, models/module.py:279-313):
+    loss = (BCE(head(cls), y) + BCE(head_dist(dist), y_teacher)) / 2; then `logits` is the pair (logits, logits_dist)."""
 
     @staticmethod
     def forward(ctx, model, mel, targets, keep_ft, t_offset, *params):
@@ -60,18 +64,34 @@ class MaestTrainStep(torch.autograd.Function):
             ops.linear(u, w16(pre + "mlp.fc2"), f32(pre + "mlp.fc2.bias"), _lib.EPI_RESID32, resid=x_mid, out=x_out)
             saved.append((x, mean1, rstd1, h1, qkv, lse, o, x_mid, mean2, rstd2, h2, upre, u))
             x = x_out
-        logits, _, feats = ops.pool_head(x, B, N, f32("norm.weight"), f32("norm.bias"), f32("head.0.weight"), f32("head.0.bias"),
-                                         f32("head.1.weight"), f32("head.1.bias"))
-        loss, dlogits = ops.bce_logits(logits, targets)
+        sep = isinstance(targets, (tuple, list))
+        if sep:
+            logits, logits_dist, feats = ops.pool_head(x, B, N, f32("norm.weight"), f32("norm.bias"), f32("head.0.weight"),
+                                                       f32("head.0.bias"), f32("head.1.weight"), f32("head.1.bias"),
+                                                       f32("head_dist.weight"), f32("head_dist.bias"), separated=True)
+            loss_s, dlogits = ops.bce_logits(logits, targets[0])
+            loss_t, dlogits_dist = ops.bce_logits(logits_dist, targets[1])
+            loss = (loss_s + loss_t) * 0.5
+            ctx.dlogits_dist = dlogits_dist
+            ctx.loss_parts = (loss_s, loss_t)
+        else:
+            logits, _, feats = ops.pool_head(x, B, N, f32("norm.weight"), f32("norm.bias"), f32("head.0.weight"), f32("head.0.bias"),
+                                             f32("head.1.weight"), f32("head.1.bias"))
+            loss, dlogits = ops.bce_logits(logits, targets)
+            ctx.dlogits_dist = None
         ctx.model, ctx.names, ctx.saved, ctx.x_final = model, names, saved, x
         ctx.dims = (B, N, int(a16.shape[0] // B), mel.shape[-1], int(t_offset))
         ctx.keep_ft, ctx.a16, ctx.dlogits = keep_ft, a16, dlogits
         ctx.params = P_
+        if sep:
+            ls_d, lt_d = loss_s.detach().clone(), loss_t.detach().clone()
+            ctx.mark_non_differentiable(logits, logits_dist, ls_d, lt_d)
+            return loss, logits, logits_dist, ls_d, lt_d
         ctx.mark_non_differentiable(logits)
         return loss, logits
 
     @staticmethod
-    def backward(ctx, dloss, _dlogits_unused):
+    def backward(ctx, dloss, *_unused):
         model, names, P_ = ctx.model, ctx.names, ctx.params
         dt = model.op_dtype
         B, N, P, T, t_off = ctx.dims
@@ -83,7 +103,8 @@ class MaestTrainStep(torch.autograd.Function):
         # parameter gradient is a view into it.  With `model.grad_allreduce` set (data-parallel run without the DDP
         # wrapper) each block's slice is all-reduced over NCCL as soon as its backward has been enqueued, so the
         # collective overlaps the remaining backward kernels; everything else about DDP stays outside.
-        gnames = [n for n in names if not n.startswith("head_dist")]
+        sep = ctx.dlogits_dist is not None
+        gnames = [n for n in names if sep or not n.startswith("head_dist")]
         offs, total = {}, 0
         for n in gnames:
             offs[n] = total
@@ -111,19 +132,29 @@ class MaestTrainStep(torch.autograd.Function):
         # fp16 operands need loss scaling (the reference's "16-mixed" uses GradScaler); bf16 does not.  The scale is applied
         # to d(loss) on the way in and divided out of the fp32 parameter gradients on the way out.
         ls = float(getattr(model, "train_loss_scale", None) or (4096.0 if ops.op_dtype_code(dt) == ops.F16 else 1.0))
-        gscale = (dloss.detach().float().reshape(1) * ls).contiguous()
+        gscale = (dloss.detach().float().reshape(1) * (ls * (0.5 if sep else 1.0))).contiguous()   # separated: loss = (l_s + l_t) / 2
         lib = _lib.init(dev.index if dev.index is not None else torch.cuda.current_device())
         st = torch.cuda.current_stream().cuda_stream
         C_ = P_["head.1.weight"].shape[0]
 
         dx = torch.zeros((M, E), device=dev, dtype=torch.float32)
         hz = torch.empty((B, E), device=dev, dtype=torch.float32)
-        _lib.check(lib.maest_head_bwd(ctx.x_final.data_ptr(), B, N, ctx.dlogits.data_ptr(), gscale.data_ptr(),
-                                      f32("norm.weight").data_ptr(), f32("norm.bias").data_ptr(), f32("head.0.weight").data_ptr(),
-                                      f32("head.0.bias").data_ptr(), f32("head.1.weight").data_ptr(), C_, dx.data_ptr(), hz.data_ptr(),
-                                      G["norm.weight"].data_ptr(), G["norm.bias"].data_ptr(), G["head.0.weight"].data_ptr(),
-                                      G["head.0.bias"].data_ptr(), G["head.1.weight"].data_ptr(), G["head.1.bias"].data_ptr(), st),
-                   "head_bwd")
+        if sep:
+            z1 = torch.empty((B, E), device=dev, dtype=torch.float32)
+            _lib.check(lib.maest_head_bwd_separated(
+                ctx.x_final.data_ptr(), B, N, ctx.dlogits.data_ptr(), ctx.dlogits_dist.data_ptr(), gscale.data_ptr(),
+                f32("norm.weight").data_ptr(), f32("norm.bias").data_ptr(), f32("head.0.weight").data_ptr(),
+                f32("head.0.bias").data_ptr(), f32("head.1.weight").data_ptr(), f32("head_dist.weight").data_ptr(), C_,
+                dx.data_ptr(), hz.data_ptr(), z1.data_ptr(), G["norm.weight"].data_ptr(), G["norm.bias"].data_ptr(),
+                G["head.0.weight"].data_ptr(), G["head.0.bias"].data_ptr(), G["head.1.weight"].data_ptr(),
+                G["head.1.bias"].data_ptr(), G["head_dist.weight"].data_ptr(), G["head_dist.bias"].data_ptr(), st), "head_bwd_separated")
+        else:
+            _lib.check(lib.maest_head_bwd(ctx.x_final.data_ptr(), B, N, ctx.dlogits.data_ptr(), gscale.data_ptr(),
+                                          f32("norm.weight").data_ptr(), f32("norm.bias").data_ptr(), f32("head.0.weight").data_ptr(),
+                                          f32("head.0.bias").data_ptr(), f32("head.1.weight").data_ptr(), C_, dx.data_ptr(), hz.data_ptr(),
+                                          G["norm.weight"].data_ptr(), G["norm.bias"].data_ptr(), G["head.0.weight"].data_ptr(),
+                                          G["head.0.bias"].data_ptr(), G["head.1.weight"].data_ptr(), G["head.1.bias"].data_ptr(), st),
+                       "head_bwd")
         reduce_range(offs["norm.weight"], total)                      # final norm + head gradients are complete
         dx16 = ops.cast_rows16(dx, M, dt)
         dh = torch.empty((M, E), device=dev, dtype=torch.float32)
@@ -180,26 +211,44 @@ class MaestTrainStep(torch.autograd.Function):
             scale /= dist.get_world_size(grp)
         if scale != 1.0:
             flat.mul_(scale)
+        if ls != 1.0 and getattr(model, "train_check_overflow", True):
+            # fp16 operands (opt-in; training defaults to bf16): the reference's "16-mixed" uses a dynamic GradScaler.  Here the
+            # scale is static, so an overflow must not reach the optimiser: zero this step's gradients (AdamW then only
+            # decays), halve the scale for the next step and say so.  One host sync per step, fp16 training only.
+            if not bool(torch.isfinite(flat).all()):
+                import warnings
+                model.train_loss_scale = ls * 0.5
+                flat.zero_()
+                warnings.warn(f"maest_b200: fp16 gradient overflow, step skipped; loss scale {ls:g} -> {ls * 0.5:g}")
         grads = tuple(G[n].to(P_[n].dtype) if n in G else None for n in names)   # head_dist.* get no gradient ("mean" mode)
         return (None, None, None, None, None) + grads
 
 
-def training_forward(model, mel: torch.Tensor, targets: torch.Tensor, mix: Optional[tuple] = None):
+def training_forward(model, mel: torch.Tensor, targets, mix: Optional[tuple] = None):
     """Train-mode forward + BCE loss with autograd support.  Host RNG draws follow the reference's order: the mixup draws
-    (if any) are made by the caller BEFORE this function (helpers/mixup.py:6-7), then time offset / patchout here."""
-    if model.distilled_type != "mean":
-        raise NotImplementedError("the fused training step implements distilled_type='mean' (every shipped training config)")
+    (if any) are made by the caller BEFORE this function (helpers/mixup.py:6-7), then time offset / patchout here.
+
+    distilled_type "mean": `targets` = y, returns (loss, logits).  distilled_type "separated" (teacher-student step,
+    models/module.py:279-313): `targets` = (y, y_teacher), returns (loss, logits, logits_dist, loss_standard, loss_teacher)."""
+    sep = model.distilled_type == "separated"
+    if model.distilled_type not in ("mean", "separated"):
+        raise ValueError(f"unknown distilled_type {model.distilled_type!r}")
+    if sep != isinstance(targets, (tuple, list)):
+        raise ValueError("distilled_type='separated' takes targets=(y, y_teacher); 'mean' takes a single target tensor")
     dev = model.cls_token.device
     if dev.type != "cuda":
         raise RuntimeError("maest_b200: training runs on CUDA (B200) only")
     mel = mel.to(dev)
-    targets = targets.to(dev)
+    targets = tuple(t.to(dev) for t in targets) if sep else targets.to(dev)
     if mel.dim() == 4:
         mel = mel[:, 0]
     if mix is not None:
         perm, lam = mix
         mel = ops.mixup(mel, perm.to(dev), lam.to(dev))
-        targets = ops.mixup(targets, perm.to(dev), lam.to(dev))
+        if sep:
+            targets = tuple(ops.mixup(t, perm.to(dev), lam.to(dev)) for t in targets)
+        else:
+            targets = ops.mixup(targets, perm.to(dev), lam.to(dev))
     if mel.shape[1] != 96:
         raise NotImplementedError(f"the B200 patch kernels take 96 mel bands, got {mel.shape[1]}")
     Fp, Tp = (mel.shape[1] - 16) // 10 + 1, (mel.shape[2] - 16) // 10 + 1

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.maest_abi_version() == 6
+    assert lib.maest_abi_version() == _lib.ABI_VERSION == 7
     assert lib.maest_encoder_workspace_bytes(1000) > 1000 * 13824
     assert lib.maest_patch_workspace_bytes(2, 558) >= 2 * 558 * 512 + 558 * 3072
 
@@ -135,3 +135,47 @@ def test_logmel_kernel_host_emulation(tmp_path):
         mel = np.frombuffer(out.stdout, dtype=np.float32).reshape(96, 1 + S // 256)
         ref = O.logmel(x, torch.float64).numpy()
         assert np.abs(mel - ref).max() < 1e-5
+
+
+def test_reference_harness_import_lines_resolve():
+    """The reference harness imports these names (ex_maest.py:19-21: `from models import get_maest`, `from models.module import
+    Module, TeacherStudentModule`); INTEGRATION.md's drop-in story needs every one of them to exist here with the same call
+    surface (constructor keywords of models/module.py:44-56, configure_callbacks :256-276)."""
+    import inspect
+    from maest_b200 import get_maest  # noqa: F401
+    from maest_b200.module import Module, StochasticWeightAveragingAndCopy, TeacherStudentModule, module_ing  # noqa: F401
+    assert issubclass(TeacherStudentModule, Module)
+    sig = inspect.signature(Module.__init__)
+    for kw in ("do_swa", "swa_epoch_start", "swa_lrs", "swa_freq", "mixup_alpha", "distributed_mode"):
+        assert kw in sig.parameters, kw
+    for meth in ("training_step", "validation_step", "test_step", "predict_step", "configure_optimizers", "configure_callbacks",
+                 "on_validation_epoch_end", "on_test_epoch_end", "get_optimizer", "get_lr_scheduler", "get_scheduler_lambda"):
+        assert callable(getattr(Module, meth)), meth
+    assert TeacherStudentModule.training_step is not Module.training_step
+    assert TeacherStudentModule.test_validation_step is not Module.test_validation_step
+
+
+def test_patchout_index_options_follow_the_reference_semantics():
+    """s_patchout_{f,t}_indices / _interleaved build their index sets from the ORIGINAL grid size and index the already-reduced
+    axis (models/maest.py:703-766): alone they select like the reference; combined with random structured patchout an index
+    past the reduced length raises IndexError exactly as torch's indexing does there."""
+    import torch
+    from maest_b200 import get_maest
+    m = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, s_patchout_t_indices=(0, 5), s_patchout_f_interleaved=2)
+    m.eval()
+    _, keep_f, keep_t, _ = m._draw_patchout(9, 62)
+    assert keep_f.tolist() == [0, 2, 4, 6, 8]
+    assert keep_t.tolist() == [i for i in range(62) if i not in (0, 5)]
+    m2 = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, s_patchout_t=30, s_patchout_t_interleaved=2)
+    m2.train()
+    torch.manual_seed(0)
+    import pytest
+    with pytest.raises(IndexError):
+        m2._draw_patchout(9, 62)      # arange(0, 62, 2) reaches index 60 of an axis that has 32 entries left
+
+
+def test_input_f_other_than_96_is_refused():
+    import pytest
+    from maest_b200 import get_maest
+    with pytest.raises(NotImplementedError):
+        get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, input_f=128)

@@ -45,7 +45,7 @@ def m30():
 
 def test_native_library_is_loaded():
     lib = _lib.init(0)
-    assert lib.maest_abi_version() == 6
+    assert lib.maest_abi_version() == _lib.ABI_VERSION
     maps = open("/proc/self/maps").read()
     assert "libmaest_b200.so" in maps
 
@@ -129,8 +129,8 @@ def test_gelu_epilogue_matches_exact_erf_gelu():
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("BN", [(1, 128), (2, 100), (2, 560), (1, 1685), (3, 866), (1, 3)])
-@pytest.mark.parametrize("variant", [0, 1, 2])
+@pytest.mark.parametrize("BN", [(1, 128), (2, 100), (2, 560), (1, 1685), (3, 866), (1, 3), (2, 129), (1, 257), (5, 200)])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 def test_attention_vs_fp64(dt, BN, variant):
     B, N = BN
     g = torch.Generator().manual_seed(B * 1000 + N)
@@ -150,8 +150,29 @@ def test_attention_sharp_scores_and_rescale_path():
     qkv.view(N, 3, 12, 64)[400:, 1] *= 3
     q, k, v = qkv.view(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4).double()
     ref = (torch.softmax((q @ k.transpose(-1, -2)) * 0.125, -1) @ v).transpose(1, 2).reshape(B * N, 768)
-    for variant in (0, 1, 2):
+    for variant in (0, 1, 2, 3, 4):
         assert rel(ops.attention(qkv, B, N, 12, variant), ref) < 1e-3
+
+
+@pytest.mark.parametrize("variant", [3, 4])
+def test_attention_chain_kernel_lse_and_exact_redo(variant):
+    """The chains kernel (default): log-sum-exp for the backward pass, and rows whose scores leave the fixed reference's range
+    (here: a few query rows scaled up so that later keys beat the first KV tile by far more than 2^16) take the exact redo."""
+    g = torch.Generator().manual_seed(5)
+    B, N = 2, 700
+    qkv = torch.randn(B * N, 2304, generator=g).half().cuda()
+    qkv.view(B * N, 3, 12, 64)[300:310, 0] *= 40          # ten sharp query rows per ... (rows 300-309 of clip 0)
+    qkv.view(B * N, 3, 12, 64)[1000:1003, 0] *= 60
+    q, k, v = qkv.view(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4).double()
+    s = (q @ k.transpose(-1, -2)) * 0.125
+    ref = (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, 768)
+    lse_ref = torch.logsumexp(s, -1) * 1.4426950408889634
+    o, lse = ops.attention(qkv, B, N, 12, variant, save_lse=True)
+    assert not torch.isnan(o.float()).any()
+    assert rel(o, ref) < 1e-3
+    assert float((lse.double() - lse_ref).abs().max()) < 2e-3
+    o2, _ = ops.attention(qkv, B, N, 12, variant, save_lse=True)
+    assert torch.equal(o, o2)
 
 
 def test_layernorm_head_embedding_units():

@@ -67,20 +67,22 @@ def child():
         ops.attention(qkv, B, N, 12, variant, save_lse=True)
         _, lse = ops.attention(qkv, B, N, 12, variant, save_lse=True)
         torch.cuda.synchronize()
-        d = lse.reshape(-1)[: 148 * 256].view(148, 256).double()
-        nq, nkv = (N + 127) // 128, (N + 127) // 128
+        nch, bkv = (3, 128) if variant == 3 else (4, 96)
+        d = lse.reshape(-1)[: 148 * 512].view(148, 512).double()
+        nq, nkv = (N + 127) // 128, (N + bkv - 1) // bkv
         tiles = B * 12 * nq * nkv / 148.0
         items = B * 12 * nq / 148.0
-        sm = d[:, :192].view(148, 12, 16).mean((0, 1))
-        names = ["wait_s", "wait_mref", "flush", "epilogue", "exp_to_arrive", "leader_max", "total", "epi_wait_lpart", "epi_wait_o", "flush_wait_oempty", "bad_rows", "epi_index_math", "epi_tmem_ld", "epi_stores"]
-        out["softmax_per_tile"] = {k: round(float(sm[i]) / (tiles / 3)) for i, k in enumerate(names[:7])}
-        out["softmax_per_item_per_chain"] = {k: round(float(sm[i]) / items, 1) for i, k in enumerate(names) if i not in (0, 4, 6)}
-        pc = d[:, :192].view(148, 3, 4, 16).mean((0, 2))       # per chain
-        out["per_chain_per_tile"] = {k: [round(float(pc[c, i]) / (tiles / 3)) for c in range(3)] for i, k in enumerate(names[:7])}
-        t = d[:, 200:204].mean(0) / tiles
+        sm = d[:, :16 * 4 * nch].view(148, 4 * nch, 16).mean((0, 1))
+        names = ["wait_s", "wait_mref", "flush", "epilogue", "exp_to_arrive", "leader_max", "total"]
+        out["tiles_per_sm"] = round(tiles)
+        out["softmax_per_tile"] = {k: round(float(sm[i]) / (tiles / nch)) for i, k in enumerate(names)}
+        out["bad_rows"] = float(sm[10])
+        t = d[:, 400:404].mean(0) / tiles
         out["tma_per_tile"] = dict(zip(["wait_kv_empty", "-", "wait_q_empty", "total"], [round(float(x)) for x in t]))
-        m = d[:, 208:214].mean(0) / tiles
-        out["mma_per_tile"] = dict(zip(["wait_q", "wait_kv", "wait_o_empty", "wait_p", "-", "total"], [round(float(x)) for x in m]))
+        q = d[:, 420:425].mean(0) / tiles
+        out["qk_issuer_per_tile"] = dict(zip(["wait_q", "wait_kv", "wait_pv_done", "issue", "total"], [round(float(x)) for x in q]))
+        m = d[:, 408:417].mean(0) / tiles
+        out["pv_issuer_per_tile"] = dict(zip(["-", "wait_kv", "wait_o_empty", "wait_p", "-", "total", "pv_issue", "-", "next"], [round(float(x)) for x in m]))
     print("ATTN2 " + json.dumps(out), flush=True)
 
 
