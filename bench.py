@@ -17,6 +17,7 @@ not exist on the GPU box, and the oracle is pinned against it by tests/golden.
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import subprocess
@@ -92,23 +93,52 @@ class ClockSampler:
         return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=sorted(reasons), samples=len(sm))
 
 
-def cpu_oracle_clips_per_s(arch: str, clips: int, repeats: int = 1):
-    """Time the CPU restatement of the reference on `clips` clips of the workload (fp32, all host threads)."""
+def cpu_forward_fn(arch: str):
+    """The CPU implementation of the path that the baseline legs time, and what it is.
+
+    Preferred: the UNMODIFIED reference (palonso/MAEST `maest` package pip-installed into baseline/_ref, see DESIGN.md section 1;
+    its two absent pure-Python imports, sacred and timm, are stubbed in memory by tests/golden/ref_loader.py) -> kind "reference".
+    Fallback when baseline/_ref did not travel: oracle/maest_oracle.py, the torch-CPU restatement pinned to it -> kind "port"."""
     import torch
     from maest_b200 import synth
-    from oracle import maest_oracle as O
 
     S, grid_t = ARCH_T[arch]
-    torch.set_num_threads(os.cpu_count() or 1)
     sd = synth.synth_state_dict(grid_t, 400, seed=0)
+    ref_dir = os.environ.get("MAEST_REF_INSTALL", os.path.join(ROOT, "baseline", "_ref"))
+    if os.path.isfile(os.path.join(ref_dir, "maest", "maest.py")) and not os.environ.get("MAEST_BENCH_FORCE_PORT"):
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+            sys.path.insert(0, ref_dir)
+            import ref_loader
+            ref_loader.install_stubs(with_lightning=True)
+            import maest as ref_pkg
+            net = ref_pkg.get_maest(arch=arch, pretrained=False)
+            net.load_state_dict(sd, strict=False)
+            net.eval()
+            return (lambda x: net(x)[0]), "reference", "unmodified reference (baseline/_ref: maest.get_maest(arch).forward, torch CPU fp32)"
+        except Exception as e:  # noqa: BLE001
+            print(f"bench.py: baseline/_ref unusable ({type(e).__name__}: {e}); timing the oracle port instead", file=sys.stderr)
+    from oracle import maest_oracle as O
+    return (lambda x: O.forward(x, sd, img_t=(S // 256), dtype=torch.float32)), "port", \
+        "oracle/maest_oracle.py (torch-CPU fp32 restatement of the reference)"
+
+
+def cpu_baseline_clips_per_s(arch: str, clips: int, repeats: int = 1):
+    """Time the reference's CPU path on `clips` clips of the workload (fp32, all host threads)."""
+    import torch
+    from maest_b200 import synth
+
+    S, _ = ARCH_T[arch]
+    torch.set_num_threads(os.cpu_count() or 1)
+    fwd, kind, what = cpu_forward_fn(arch)
     x = synth.wave_a(clips, S)
     best = float("inf")
     with torch.no_grad():
         for _ in range(repeats):
             t0 = time.perf_counter()
-            O.forward(x, sd, img_t=(S // 256), dtype=torch.float32)
+            fwd(x.clone())
             best = min(best, time.perf_counter() - t0)
-    return clips / best, torch.get_num_threads()
+    return clips / best, torch.get_num_threads(), kind, what
 
 
 def run_reference(args):
@@ -119,27 +149,26 @@ def run_reference(args):
     os.environ["MKL_NUM_THREADS"] = str(os.cpu_count() or 1)
     import torch
     from maest_b200 import synth
-    from oracle import maest_oracle as O
 
     S, grid_t = ARCH_T[args.arch]
     clips = args.ref_clips
     torch.set_num_threads(os.cpu_count() or 1)
-    sd = synth.synth_state_dict(grid_t, 400, seed=0)
+    fwd, kind, what = cpu_forward_fn(args.arch)
     x = synth.wave_a(clips, S)
     with torch.no_grad():
         for _ in range(args.warmup):
-            O.forward(x, sd, img_t=S // 256, dtype=torch.float32)
+            fwd(x.clone())           # (the reference unsqueezes its input in place)
         t0 = time.perf_counter()
         for _ in range(args.steps):
-            O.forward(x, sd, img_t=S // 256, dtype=torch.float32)
+            fwd(x.clone())
         dt = time.perf_counter() - t0
     val = clips * args.steps / dt
     N = 2 + 9 * ((S // 256 + 1 - 16) // 10 + 1)
     line = dict(metric="clips/sec", value=val, unit="clips/s", impl="reference", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
                 ms_per_step=1e3 * dt / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=f"{args.arch} inference, waveform [{clips},{S}] -> logits, N={N} tokens (bounded CPU sample of the batch-64 workload)"),
-                cpu_baseline=dict(value=val, unit="clips/s", cores=torch.get_num_threads(), kind="port",
-                                  sample=f"{clips} clips/step x {args.steps} steps, oracle/maest_oracle.py fp32 torch-CPU restatement of the reference"),
+                cpu_baseline=dict(value=val, unit="clips/s", cores=torch.get_num_threads(), kind=kind,
+                                  sample=f"{clips} clips/step x {args.steps} steps, {what}"),
                 e2e=dict(value=val, unit="clips/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line), flush=True)
 
@@ -221,25 +250,39 @@ def kernel_breakdown(model, wav, iters: int = 3):
 
 
 def run_train(args):
+    """--mode train: only the training leg (see train_leg), printed as its own JSON line."""
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = train_leg(args, args.steps, args.warmup, args.batch)
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def train_leg(args, steps: int, warmup: int, B: int):
     """configs[3]: maest_30s_from_passt_pretrain training step (mel [B,1,96,1875] fp16 in, s_patchout_t=90 -> 866 tokens,
-    mixup 0.3, BCE), bf16 operands, fwd + bwd + gradient all-reduce (N>1) + AdamW step inside the timed region."""
+    mixup 0.3, BCE), bf16 operands, fwd + bwd + gradient all-reduce (N>1) + AdamW step inside the timed region.
+    The process group (N>1) is the caller's.  Returns the JSON line (rank 0) / None."""
     import numpy as np
     import torch
     import torch.distributed as dist
     from maest_b200 import get_maest, synth
-    from maest_b200.module import Module, allreduce_gradients
+    from maest_b200.module import Module
 
     rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    B = args.batch
     op = "bf16" if args.op_dtype == "fp16" and not os.environ.get("MAEST_TRAIN_FP16") else args.op_dtype
     net = get_maest(arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=400, input_f=96, input_t=1875, s_patchout_t=90, op_dtype=op)
     net.load_state_dict(synth.synth_state_dict(187, 400, seed=0), strict=False)
     if world > 1:
-        net.grad_allreduce = True          # per-block NCCL all-reduce of the flat gradient buffer, overlapped with backward
+        net.grad_allreduce = True          # ONE flat fp32 NCCL all-reduce of the gradient buffer after the last backward kernel
+    net.allreduce_events = []              # (start, end) CUDA events around that all-reduce, one pair per step (train.py)
     mod = Module(net=net, mixup_alpha=0.3, do_swa=False).to(dev).train()
     from maest_b200.optim import FusedAdamW
     opt = FusedAdamW(mod.parameters(), lr=2e-5, weight_decay=1e-4)      # one launch for all 152 parameter tensors
@@ -255,12 +298,12 @@ def run_train(args):
         opt.zero_grad(set_to_none=True)
         loss = mod.training_step(batch, 0)
         loss.backward()
-        if world > 1:
+        if not n_grad[0]:
             n_grad[0] = sum(p.numel() for p in mod.parameters() if p.grad is not None)
         opt.step()
         return loss
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -268,9 +311,10 @@ def run_train(args):
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
+    net.allreduce_events.clear()
     e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
     e0.record()
-    for _ in range(args.steps):
+    for _ in range(steps):
         loss = step()
     e1.record()
     if world > 1:
@@ -282,24 +326,33 @@ def run_train(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    ar_ms = [a.elapsed_time(b) for a, b in net.allreduce_events]
+    ar_ms = sum(ar_ms) / len(ar_ms) if ar_ms else 0.0
+    if world > 1:
+        t = torch.tensor([ar_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ar_ms = float(t.item())
+    line = None
     if rank == 0:
         N, P = 866, 864
         fl = flops_per_clip(N, P)
         peaks = measured_peaks()
-        value = B * world * args.steps / (ms / 1e3)
+        value = B * world * steps / (ms / 1e3)
         tf = value / world * 3 * fl["total"] / 1e12
-        line = dict(metric="clips/sec (training step)", value=value, unit="clips/s", n_gpus=world, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=ms / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+        line = dict(metric="clips/sec (training step)", value=value, unit="clips/s", n_gpus=world, steps=steps, warmup=warmup,
+                    ms_per_step=ms / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                     dtype=op + " operands, fp32 master weights/accumulate/residual/softmax", data="synthetic", mode="train",
                     config=dict(workload=f"maest_30s_from_passt_pretrain training step: mel [{B},1,96,1875] fp16 per GPU, s_patchout_t=90 -> {N} tokens, "
                                          "mixup 0.3, BCE, fwd+bwd" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + AdamW step",
                                 batch_per_gpu=B, tokens=N, gflop_per_clip_fwd=fl["total"] / 1e9),
-                    loss=float(loss.detach()), grad_elements_allreduced=n_grad[0], clocks=clocks,
+                    loss=float(loss.detach()), grad_elements_allreduced=n_grad[0], allreduce_bytes=4 * n_grad[0],
+                    allreduce_ms_exposed=ar_ms, allreduce="one flat fp32 dist.all_reduce (NCCL) after the last backward kernel, not overlapped"
+                    if world > 1 else "none (1 GPU)", clocks=clocks,
                     model_tflops=tf, model_frac_of_bf16_sustained=tf / peaks["bf16_tflops_sustained"],
-                    gpu_launches=args.steps * (12 * 30 + 12))
-        print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+                    gpu_launches=steps * (12 * 30 + 12))
+    del mod, net, opt
+    torch.cuda.empty_cache()
+    return line
 
 
 def run_ingest(args):
@@ -388,6 +441,8 @@ def main():
     ap.add_argument("--cpu-baseline-clips", type=int, default=4)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-breakdown", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=5, help="default (infer) mode: timed steps of the configs[3] training leg reported "
+                                                               "under the `train` key (0 = skip)")
     ap.add_argument("--mode", default="infer", choices=["infer", "train", "ingest"],
                     help="infer: BASELINE.json configs[2] (headline).  train: configs[3], one optimisation step per 'step'.  "
                          "ingest: loader -> device ingest kernel (SURVEY.md section 8(f) row 1)")
@@ -419,6 +474,7 @@ def main():
     B = args.batch
     model = get_maest(arch=args.arch, pretrained=False, op_dtype=args.op_dtype, fuse_ln=args.fuse_ln)
     model.attn_variant = args.attn_variant
+    model_attn_variant = args.attn_variant
     model.load_state_dict(synth.synth_state_dict(grid_t, 400, seed=0), strict=False)   # random-init weights (no checkpoints offline)
     model = model.to(dev).eval()
 
@@ -499,6 +555,12 @@ def main():
         if rank == 0 and not args.no_breakdown:
             breakdown = kernel_breakdown(model, wav_dev)
 
+    # ---------------- configs[3] training leg (every rank; gradient all-reduce over NCCL at N > 1) ----------------
+    train_line = None
+    if args.train_steps > 0:
+        del model, stage, wav_dev
+        torch.cuda.empty_cache()
+        train_line = train_leg(args, args.train_steps, 3, B)
     if world > 1:
         dist.barrier()
     if rank != 0:
@@ -532,20 +594,34 @@ def main():
         achieved = gemm_flops / (gemm_ms / 1e3) / 1e12
         total_ms = sum(v["ms_per_step"] for v in breakdown.values())
         traffic = None
-        import glob
         tfiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_gemm_traffic.json")))      # newest round's ncu capture
         tpath = tfiles[-1] if tfiles else ""
         if os.path.exists(tpath) and B == 64 and args.arch == "discogs-maest-30s-pw-129e":
             with open(tpath) as tf:
                 traffic = json.load(tf)["gemm_family_bytes_per_step"] / gemm_launches    # measured DRAM bytes per launch (ncu --set full)
-        line["roofline"] = dict(bound="tensor", kernel="gemm_tn_kernel (qkv/proj/fc1/fc2, 48 launches per step)", achieved=achieved,
+        line["gemm_family"] = dict(bound="tensor", kernel="gemm_tn_kernel / gemm2_tn_kernel (qkv/proj/fc1/fc2, 48 launches per step)", achieved=achieved,
                                 peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s", frac=achieved / peaks["bf16_tflops_sustained"],
                                 traffic=traffic, algorithmic_flops_per_launch=gemm_flops / gemm_launches,
                                 algorithmic_bytes_per_launch=B * N * (2 * (768 + 2304) + 2 * 768 + 8 * 768 + 2 * (768 + 3072) + 2 * 3072 + 8 * 768) / 4, peak_source=peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)",
                                 share_of_step=gemm_ms / total_ms, launches_per_step=gemm_launches)
         att = breakdown.get("attention")
         if att:
+            # top-level roofline = the DOMINANT kernel: the attention forward is the largest single kernel of the step (12 launches)
+            # and the one furthest below its roofline; the GEMM family's numbers stay under `gemm_family`.
             a_tf = B * fl["attention"] / (att["ms_per_step"] / 1e3) / 1e12
+            a_traffic = None
+            afiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_attention_traffic.json")))
+            if afiles and B == 64 and args.arch == "discogs-maest-30s-pw-129e":
+                with open(afiles[-1]) as tf:
+                    a_traffic = json.load(tf).get("dram_bytes_per_launch")
+            kname = {0: "attention_fwd_spec_kernel", 3: "attention_fwd_chain_kernel<3 x 128>", 4: "attention_fwd_chain_kernel<4 x 96>",
+                     5: "attention_fwd_chain_kernel<3 x 128, split columns>"}.get(model_attn_variant, f"attention variant {model_attn_variant}")
+            line["roofline"] = dict(bound="tensor", kernel=f"{kname} (12 launches per step)", achieved=a_tf,
+                                    peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s", frac=a_tf / peaks["bf16_tflops_sustained"],
+                                    traffic=a_traffic, algorithmic_flops_per_launch=B * fl["attention"] / DEPTH,
+                                    algorithmic_bytes_per_launch=B * N * (3 * EMBED + EMBED) * 2,
+                                    ms_per_launch=att["ms_per_launch"], share_of_step=att["ms_per_step"] / total_ms, launches_per_step=DEPTH,
+                                    peak_source=peaks["source"] + " bf16_tflops_sustained (kernel timed inside a long step)")
             line["attention"] = dict(achieved=a_tf, unit="TFLOP/s", frac=a_tf / peaks["bf16_tflops_sustained"], share_of_step=att["ms_per_step"] / total_ms)
         lm = breakdown.get("logmel")
         pt = breakdown.get("patch_tokens")
@@ -555,10 +631,21 @@ def main():
             line["mel_patch_stage"] = dict(bound="hbm", achieved=gbs, peak=peaks["hbm_gbs"], unit="GB/s", frac=gbs / peaks["hbm_gbs"],
                                            algorithmic_bytes_per_clip=4 * S + 2 * N * EMBED)
         line["breakdown_ms_per_step"] = {k: round(v["ms_per_step"], 4) for k, v in breakdown.items()}
+    if train_line:
+        line["train"] = {k: train_line[k] for k in ("value", "unit", "ms_per_step", "steps", "dtype", "allreduce_bytes", "allreduce_ms_exposed",
+                                                    "allreduce", "grad_elements_allreduced", "loss", "model_frac_of_bf16_sustained", "gpu_launches")}
+        line["train"]["workload"] = train_line["config"]["workload"]
     if not args.no_cpu_baseline:
-        v, cores = cpu_oracle_clips_per_s(args.arch, args.cpu_baseline_clips)
-        line["cpu_baseline"] = dict(value=v, unit="clips/s", cores=cores, kind="port",
-                                    sample=f"{args.cpu_baseline_clips} clips of the same workload, oracle/maest_oracle.py (torch-CPU fp32 restatement of the reference), 1 run")
+        v, cores, kind, what = cpu_baseline_clips_per_s(args.arch, args.cpu_baseline_clips)
+        line["cpu_baseline"] = dict(value=v, unit="clips/s", cores=cores, kind=kind,
+                                    sample=f"{args.cpu_baseline_clips} clips of the same workload, {what}, 1 run")
+    ifiles = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_incumbent.json")))
+    if ifiles:      # torch eager / library FMHA on the same B200, measured by tools/incumbent.py in a separate session (not timed here)
+        with open(ifiles[-1]) as f:
+            inc = json.load(f)
+        line["incumbent_gpu"] = dict(source=os.path.relpath(ifiles[-1], ROOT), eager_impl=inc.get("eager_impl"),
+                                     eager_clips_per_s={k: round(v["clips_per_s"], 1) for k, v in inc.get("eager_gpu", {}).items()},
+                                     attention_ms={k: round(v["ms"], 4) for k, v in inc.get("attention_B64_H12_N1685_d64", {}).items() if "ms" in v})
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

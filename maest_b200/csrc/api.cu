@@ -197,6 +197,7 @@ int init_dt() {
   if ((r = set_smem(attention_bwd_kernel<DT>, ATTB_SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg3>, AtcCfg3::SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg4>, AtcCfg4::SMEM_BYTES))) return r;
+  if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg3x2>, AtcCfg3x2::SMEM_BYTES))) return r;
   return 0;
 }
 
@@ -441,18 +442,22 @@ int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, i
       else attention_fwd_kernel<DT_F16, true><<<grid, ATT_THREADS, att_smem_bytes<true>(), st>>>(tq, p);
       break;
     case 3:    // chains kernel, 3 chains x 128 keys (attention_chain.cuh); needs >= 2 KV tiles per item
-    case 4: {  // chains kernel, 4 chains x 96 keys
-      const int bkv = variant == 3 ? AtcCfg3::BKV : AtcCfg4::BKV;
-      const int nkv_max = variant == 3 ? AtcCfg3::NKV_MAX : AtcCfg4::NKV_MAX;
+    case 4:    // chains kernel, 4 chains x 96 keys
+    case 5: {  // chains kernel, 3 chains x 128 keys, two softmax warps per (chain, lane quadrant) splitting the columns
+      const int bkv = variant == 4 ? AtcCfg4::BKV : AtcCfg3::BKV;
+      const int nkv_max = variant == 4 ? AtcCfg4::NKV_MAX : variant == 5 ? AtcCfg3x2::NKV_MAX : AtcCfg3::NKV_MAX;
       if (N <= bkv || (N + bkv - 1) / bkv > nkv_max) return maest_attention_fwd(qkv, out, lse, B, N, H, op_dtype, 0, stream);
       const int items = B * H * ((N + ATT_BQ - 1) / ATT_BQ);
       const int sms = g_num_sms[cur_device()];
       const int g = items < sms ? items : sms;
       CUtensorMap tkv;
-      if ((r = make_tmap(&tkv, qkv, op_dtype, uint64_t(B) * N, uint64_t(3) * H * ATT_D, uint64_t(3) * H * ATT_D, bkv))) return r;
+      if ((r = make_tmap(&tkv, qkv, op_dtype, uint64_t(B) * N, uint64_t(3) * H * ATT_D, uint64_t(3) * H * ATT_D, bkv / ATC_LOADDIV))) return r;
       if (variant == 3) {
         if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg3><<<g, AtcCfg3::THREADS, AtcCfg3::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
         else attention_fwd_chain_kernel<DT_F16, AtcCfg3><<<g, AtcCfg3::THREADS, AtcCfg3::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+      } else if (variant == 5) {
+        if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg3x2><<<g, AtcCfg3x2::THREADS, AtcCfg3x2::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+        else attention_fwd_chain_kernel<DT_F16, AtcCfg3x2><<<g, AtcCfg3x2::THREADS, AtcCfg3x2::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
       } else {
         if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg4><<<g, AtcCfg4::THREADS, AtcCfg4::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
         else attention_fwd_chain_kernel<DT_F16, AtcCfg4><<<g, AtcCfg4::THREADS, AtcCfg4::SMEM_BYTES, st>>>(tq, tkv, p, qkv);

@@ -39,25 +39,47 @@ namespace mb {
 // Registers: the CTA launches with the whole file split evenly, the helper warpgroup gives most of its share back
 // (setmaxnreg.dec) and the softmax warpgroups take it (setmaxnreg.inc).  With spills the kernel was 30 % slower: the L1 that
 // backs local memory is only ~30 KB when ~200 KB of shared memory are configured, so spill reloads went to L2.
-template <int NCH_, int BKV_, int CW_, int R_, int REGS_SM_, int REGS_AUX_, int NKV_MAX_>
+// NSPLIT = 2: TWO softmax warps per (chain, TMEM lane quadrant), each owning half of the tile's score columns (its packed P stays
+// inside its own half: PV reads k-steps 0..3 from the first half, 4..7 from the second).  Six instead of three softmax warps per
+// sub-partition: the per-tile dependency chain S -> exp -> P of a chain is half as long and the sub-partition always has a warp
+// to issue from (r02 phase clocks: with one warp per chain the softmax warps kept their sub-partition 42 % busy).
+template <int NCH_, int BKV_, int CW_, int R_, int REGS_SM_, int REGS_AUX_, int NKV_MAX_, int NSPLIT_ = 1>
 struct AtcCfgT {
-  static constexpr int NCH = NCH_, BKV = BKV_, CW = CW_, R = R_, REGS_SM = REGS_SM_, REGS_AUX = REGS_AUX_;
-  static constexpr int THREADS = (4 * NCH + 4) * 32;
+  static constexpr int NCH = NCH_, BKV = BKV_, CW = CW_, R = R_, REGS_SM = REGS_SM_, REGS_AUX = REGS_AUX_, NSPLIT = NSPLIT_;
+  static constexpr int HW = BKV / NSPLIT;                  // score columns owned by one softmax warp
+  static constexpr bool PINGPONG = NSPLIT == 1;            // two register chunks in flight (one warp per chain and quadrant needs the
+                                                           // overlap; with split columns the other warps cover the tcgen05.ld latency)
+  static constexpr int THREADS = (4 * NCH * NSPLIT + 4) * 32;
   static constexpr int KV_BYTES = BKV * ATT_D * 2;
   static constexpr int SLOT_BYTES = 2 * KV_BYTES;
   static constexpr int NBAR = 2 + 2 + 2 * R + 3 * NCH + 2 + 2 + 2 + 2;
   static constexpr int OFF_KV = 2 * ATT_TILE_BYTES;
   static constexpr int OFF_BAR = OFF_KV + R * SLOT_BYTES;
   static constexpr int OFF_MREF = OFF_BAR + ((NBAR * 8 + 16 + 127) / 128) * 128;
-  static constexpr int OFF_LPART = OFF_MREF + 2 * 128 * 4;
+  static constexpr int OFF_LPART = OFF_MREF + 2 * NSPLIT * 128 * 4;
   static constexpr int NKV_MAX = NKV_MAX_;      // KV tiles per item the per-tile row-sum slots are sized for
-  static constexpr int SMEM_BYTES = OFF_LPART + 2 * NKV_MAX * 128 * 4;
+  static constexpr int SMEM_BYTES = OFF_LPART + 2 * NKV_MAX * NSPLIT * 128 * 4;
   static_assert(NCH * BKV + 128 <= 512, "TMEM: NCH score buffers + two O accumulators");
   static_assert(BKV % 32 == 0 && (CW == 32 || CW == 16), "tile / chunk shape");
+  static_assert(NSPLIT == 1 || (NSPLIT == 2 && HW % 32 == 0), "column split");
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
 };
 using AtcCfg3 = AtcCfgT<3, 128, 32, 5, 152, 56, 24>;     // 512 threads: 3 x 128 x 152 + 128 x 56 = 65 536 registers
 using AtcCfg4 = AtcCfgT<4, 96, 16, 6, 104, 56, 32>;      // 640 threads: 4 x 128 x 104 + 128 x 56 = 60 416 registers
+#ifndef ATC_X2_REGS_SM
+#define ATC_X2_REGS_SM 80
+#define ATC_X2_REGS_AUX 24
+#endif
+#ifndef ATC_X2_CW
+#define ATC_X2_CW 16
+#endif
+using AtcCfg3x2 = AtcCfgT<3, 128, ATC_X2_CW, 5, ATC_X2_REGS_SM, ATC_X2_REGS_AUX, 16, 2>;   // 896 threads: 6 x 128 x 80 + 128 x 24 = 64 512 registers
 
+// ATC_LOADDIV = 2 (timing diagnostic only, results are garbage): every K / V load fetches only the first half of the tile's rows
+// (the rest of the zero-initialised ring slot stays zero) -- tells whether the kernel is bound by L2 -> SM bandwidth.
+#ifndef ATC_LOADDIV
+#define ATC_LOADDIV 1
+#endif
 #ifdef ATC_DIAG   // timing diagnostic: per-role wait clocks, written over p.lse[blockIdx.x * 512 + ...] (the lse values are garbage)
 #define ATC_T0() unsigned t__ = (unsigned)clock()
 #define ATC_ACC(var) do { const unsigned n__ = (unsigned)clock(); var += n__ - t__; t__ = n__; } while (0)
@@ -128,11 +150,12 @@ __device__ __forceinline__ void mma_qk4(uint32_t tS, uint64_t qd, uint64_t kd, u
       : "memory");
 }
 // O[tO] (+)= P[tP] V: KS steps of K = 16 (P advances 8 TMEM columns, V 16 rows = 2048 B = +128 per step); acc0 = 0 starts an item.
-template <int KS>
+// KH = k-steps per column half (KS when the tile is not split): the packed P of half h starts at column h * 16 * KH.
+template <int KS, int KH>
 __device__ __forceinline__ void mma_pv(uint32_t tO, uint32_t tP, uint64_t vd, uint32_t idesc, uint32_t acc0) {
   mma_ts(tO, tP, vd, idesc, acc0);
 #pragma unroll
-  for (int k = 1; k < KS; ++k) mma_ts(tO, tP + uint32_t(8 * k), vd + uint64_t(128 * k), idesc, 1u);
+  for (int k = 1; k < KS; ++k) mma_ts(tO, tP + uint32_t((k / KH) * (16 * KH) + 8 * (k % KH)), vd + uint64_t(128 * k), idesc, 1u);
 }
 
 // W score columns -> W/2 packed P words, IN PLACE: P word i (columns 2i, 2i+1) replaces s[i], which pair i/2 has already consumed
@@ -148,8 +171,8 @@ __device__ __forceinline__ void att_chain_chunk(uint32_t (&s)[W], u64& la, u64& 
     if (true) {
       float a0, a1;
       f2_unpack(a, a0, a1);
-      p0 = a0 * 1e-3f;
-      p1 = a1 * 1e-3f;
+      p0 = fabsf(a0) * 1e-3f + 1e-3f;      // positive and finite: the row sums stay valid, no exact redo
+      p1 = fabsf(a1) * 1e-3f + 1e-3f;
     } else
 #endif
     if ((i & 7) >= 8 - NPOLY) {
@@ -283,7 +306,8 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
   using O16 = Op16<DT>;
   constexpr int NCH = Cfg::NCH, BKV = Cfg::BKV, CW = Cfg::CW, R = Cfg::R;
   constexpr int KV_BYTES = Cfg::KV_BYTES, SLOT_BYTES = Cfg::SLOT_BYTES;
-  constexpr int SMW = 4 * NCH;              // softmax warps
+  constexpr int NSPLIT = Cfg::NSPLIT, HW = Cfg::HW, KH = HW / 16;
+  constexpr int SMW = 4 * NCH * NSPLIT;     // softmax warps
   uint8_t* sQ = smem;                       // [2]
   uint8_t* sKV = smem + Cfg::OFF_KV;        // [R] slots of {K tile, V tile}: the slot of "virtual tile" vg holds K(vg) and V(vg - NCH)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -299,8 +323,8 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
   uint64_t* mref_full = o_empty + 2;        // [2]    m_ref of the item published (4 arrivals)
   uint64_t* lpart_full = mref_full + 2;     // [2]    the row sums of all tiles of the item are in shared memory (one arrival: PV issuer)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(lpart_full + 2);
-  float* s_mref = reinterpret_cast<float*>(smem + Cfg::OFF_MREF);     // [2][128]
-  float* s_lpart = reinterpret_cast<float*>(smem + Cfg::OFF_LPART);   // [2][NKV_MAX][128]: row sum of tile j of the item
+  float* s_mref = reinterpret_cast<float*>(smem + Cfg::OFF_MREF);     // [2][NSPLIT][128]
+  float* s_lpart = reinterpret_cast<float*>(smem + Cfg::OFF_LPART);   // [2][NKV_MAX][NSPLIT][128]: row sum of (tile j, column half) of the item
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -312,6 +336,10 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
   const int n_local = (n_items - int(blockIdx.x) + int(gridDim.x) - 1) / int(gridDim.x);
   const int n_tiles = n_local * nkv;
 
+  if (ATC_LOADDIV > 1) {
+    for (int i = threadIdx.x; i < R * SLOT_BYTES / 4; i += Cfg::THREADS) reinterpret_cast<uint32_t*>(sKV)[i] = 0u;
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   if (threadIdx.x == 0) {
     if ((smem_u32(smem) & 1023u) != 0) {
       printf("attention: dynamic smem base not 1024-aligned\n");
@@ -321,12 +349,12 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       mbar_init(&q_full[i], 1);
       mbar_init(&q_empty[i], 1);
       mbar_init(&o_full[i], 1);
-      mbar_init(&o_empty[i], 4);
-      mbar_init(&mref_full[i], 4);
+      mbar_init(&o_empty[i], 4 * NSPLIT);
+      mbar_init(&mref_full[i], 4 * NSPLIT);
       mbar_init(&lpart_full[i], 1);
     }
     for (int i = 0; i < R; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
-    for (int i = 0; i < NCH; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < NCH; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4 * NSPLIT); mbar_init(&pv_done[i], 1); }
     fence_mbar_init();
   }
   if (warp == SMW + 1) {
@@ -364,7 +392,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       ATC_ACC(d_kw);
       if (elect_one()) {
         uint8_t* dst = sKV + slot * SLOT_BYTES;
-        mbar_expect_tx(&kv_full[slot], (has_k ? KV_BYTES : 0) + (has_v ? KV_BYTES : 0));
+        mbar_expect_tx(&kv_full[slot], ((has_k ? KV_BYTES : 0) + (has_v ? KV_BYTES : 0)) / ATC_LOADDIV);
         if (has_v) tma_load_2d(dst + KV_BYTES, &tmap_kv, &kv_full[slot], (2 * p.H + vit.h) * ATT_D, vit.b * p.N + vj * BKV);
         if (has_k) {
           if (kj == 0) {
@@ -422,11 +450,12 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       const bool last = (j == nkv - 1);
       if (elect_one()) {
         if (!last) {
-          mma_pv<BKV / 16>(tO, tP, vd, idesc_pv, uint32_t(j));
+          mma_pv<BKV / 16, KH>(tO, tP, vd, idesc_pv, uint32_t(j));
         } else {
           const int ksteps = nc_last >> 4;
 #pragma unroll 1
-          for (int k = 0; k < ksteps; ++k) mma_ts(tO, tP + uint32_t(8 * k), vd + uint64_t(k * 128), idesc_pv, (j | k) ? 1u : 0u);
+          for (int k = 0; k < ksteps; ++k)
+            mma_ts(tO, tP + uint32_t((k / KH) * (16 * KH) + 8 * (k % KH)), vd + uint64_t(k * 128), idesc_pv, (j | k) ? 1u : 0u);
           tc_commit(&o_full[n & 1]);
         }
         tc_commit(&pv_done[c]);
@@ -500,9 +529,10 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
   } else {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_SM));
     // ------------------------------------------------------------------ softmax chains: thread <-> query row (TMEM lane)
-    const int c = warp >> 2;
+    const int c = warp / (4 * NSPLIT);
+    const int half = (warp >> 2) % NSPLIT;                 // which HW-column part of the chain's tiles this warp owns
     const int row = (warp & 3) * 32 + lane;
-    const uint32_t tS = tmem_base + uint32_t(c * BKV) + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t tS = tmem_base + uint32_t(c * BKV + half * HW) + (uint32_t((warp & 3) * 32) << 16);
     const float sc = p.scale_log2;
     const u64 sc2 = f2_packf(sc, sc);
     int cur_n = -1;
@@ -510,22 +540,31 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     const long long d_start = clock64();
     (void)d_start;
     float m_ref = 0.f;
-    AtcStep step;
-    step.init(int(gridDim.x), nq, p.H);
-    AtcItem cur_it = step.first(int(blockIdx.x)), prev_it = cur_it;   // coordinates of items cur_n (0 before the first tile) / cur_n - 1
     int n_bad = 0;
+    // coordinates of this CTA's item n, recomputed where they are needed (once per epilogue) instead of carried in registers
+    auto item_of = [&](const int n) {
+      const int it = int(blockIdx.x) + n * int(gridDim.x);
+      AtcItem x;
+      x.qt = it % nq;
+      const int r = it / nq;
+      x.h = r % p.H;
+      x.b = r / p.H;
+      return x;
+    };
     // item n (coordinates `x`): O / l -> 16-bit, log-sum-exp.  Rows the fast path could not represent get a NaN sentinel in
     // their first output word and are recomputed exactly after the main loop (keeps the function call and its register
     // traffic out of the pipelined part of the kernel).
-    auto epilogue = [&](const int n, const AtcItem x) {
+    auto epilogue = [&](const int n) {
+      const AtcItem x = item_of(n);
       const int par = n & 1;
       const uint32_t ph = (n >> 1) & 1;
       mbar_wait(&lpart_full[par], ph);
       // the tiles' row sums are added in tile order, whichever chain produced them: the result does not depend on how this
       // CTA's items happened to line up with the chains (a clip computed alone or inside a batch gives identical bits)
       float l = 0.f;
-      for (int k = 0; k < nkv; ++k) l += s_lpart[(par * Cfg::NKV_MAX + k) * 128 + row];
-      const float mr = s_mref[par * 128 + row];
+      for (int k = 0; k < nkv * NSPLIT; ++k) l += s_lpart[(par * Cfg::NKV_MAX * NSPLIT + k) * 128 + row];
+      float mr = s_mref[par * NSPLIT * 128 + row];
+      if (NSPLIT > 1) mr = fmaxf(mr, s_mref[(par * NSPLIT + 1) * 128 + row]);
       mbar_wait(&o_full[par], ph);
       tc_fence_after();
       const uint32_t tO = tmem_base + 384u + uint32_t(par) * 64u + (uint32_t((warp & 3) * 32) << 16);
@@ -534,26 +573,29 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       bool good = (l > 0.f) && (l < INFINITY);
       typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.out) + size_t(x.b * p.N + qrow) * p.ld_out + x.h * ATT_D;
       if (qrow < p.N && p.lse != nullptr) p.lse[(size_t(x.b) * p.H + x.h) * p.N + qrow] = mr + log2f(l);
+      // the 64 columns of O in parts of 32: both when the warp owns whole rows, part `half` when the columns are split
 #pragma unroll
-      for (int half = 0; half < 2; ++half) {
+      for (int q = 0; q < 2 / NSPLIT; ++q) {
+        const int oh = half * (2 / NSPLIT) + q;
         uint32_t v[32];
-        tmem_ld32(tO + uint32_t(half * 32), v);
+        tmem_ld32(tO + uint32_t(oh * 32), v);
         tc_wait_ld();
-        if (half == 1) {
+        if (q == 2 / NSPLIT - 1) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&o_empty[par]);       // O, m_ref and the l partials of this slot are in registers
         }
         // one column suffices for the finiteness test: an inf / NaN in a row of P reaches all 64 columns of that row of O
-        if (half == 0) {
+        // (the warp that owns column 0 decides, sets the sentinel and later redoes the WHOLE row)
+        if (oh == 0) {
           good = good && (fabsf(__uint_as_float(v[0]) * inv_l) < INFINITY);
           if (!good && qrow < p.N) ++n_bad;   // the first output word of the row becomes the NaN sentinel 0x7fff7fff
         }
         if (qrow < p.N) {
 #pragma unroll
           for (int i = 0; i < 32; i += 8)
-            st_global_v4(dst + half * 32 + i,
-                         (half == 0 && i == 0 && !good) ? 0x7fff7fffu : O16::pack(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
+            st_global_v4(dst + oh * 32 + i,
+                         (oh == 0 && i == 0 && !good) ? 0x7fff7fffu : O16::pack(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
                          O16::pack(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
                          O16::pack(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
                          O16::pack(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
@@ -563,17 +605,19 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     // Masked keys (past the end of the clip, last KV tile only) get the score that maps to a = -120: p = 2^-120 is zero for
     // every purpose (0 in fp16, 7.5e-37 in bf16 against row sums >= 1) and stays inside the polynomial path's valid range.
     const float inv_sc = 1.0f / sc;
+    // The epilogue of item n - 1 runs after tile epi_j of item n: the same chain as tile 1 (whose predecessor's PV is the
+    // item's last), one chain round later when the item is long enough -- by then that PV has long retired (r02 clocks: at tile 1
+    // the epilogue still waited ~3000 cycles for o_full).
+    const int epi_j = nkv > 1 + NCH ? 1 + NCH : 1;
     int n = 0, j = c;
     while (j >= nkv) { j -= nkv; ++n; }
     // NCH "virtual" tiles past the end give every chain one more pass through the item-change / epilogue logic below, so the
     // flush and the epilogue have exactly one call site each.
 #pragma unroll 1
-    for (int g = c; g < n_tiles + NCH; g += NCH) {
+    for (int g = c; g < n_tiles + 2 * NCH; g += NCH) {
       bool new_item = false;
       ATC_T0();
       if (n != cur_n) {
-        int k = cur_n < 0 ? 0 : cur_n;
-        while (k < n) { prev_it = cur_it; step.next(cur_it); ++k; }    // cur_it = item n, prev_it = item n - 1
         cur_n = n;
         new_item = true;
         // the row-sum and m_ref slots of this parity were last read by the epilogue of item n - 2
@@ -582,8 +626,9 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       ATC_ACC(d_flush);
       if (g < n_tiles) {
         const bool last = (j == nkv - 1);
-        const int ncols = last ? nc_last : BKV;
-        const int valid = last ? valid_last : BKV;
+        // this warp's columns [half * HW, half * HW + ncols) of the tile, the first `valid` of them real keys
+        const int ncols = max(0, min(HW, (last ? nc_last : BKV) - half * HW));
+        const int valid = max(0, min(HW, (last ? valid_last : BKV) - half * HW));
         mbar_wait(&s_full[c], ((g - c) / NCH) & 1);
         ATC_ACC(d_s);
         tc_fence_after();
@@ -594,7 +639,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
           // this chain owns the item's first tile (never the ragged last one: nkv >= 2): exact row max -> the item's reference
           float mx = -INFINITY;
 #pragma unroll 1
-          for (int col = 0; col < BKV; col += CW) {
+          for (int col = 0; col < HW; col += CW) {
             ca.ld(tS + uint32_t(col));
             tc_wait_ld();
             ca.fence();
@@ -607,14 +652,17 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
             mx = fmaxf(mx, fmaxf(m0, m1));
           }
           m_ref = mx * sc;
-          s_mref[(n & 1) * 128 + row] = m_ref;
+          s_mref[((n & 1) * NSPLIT + half) * 128 + row] = m_ref;
           __syncwarp();
           if (lane == 0) mbar_arrive(&mref_full[n & 1]);
           ATC_ACC(d_lead);
-        } else if (new_item) {
-          // first tile of this chain in the item: pick the reference up
+        }
+        if (j == 0 ? NSPLIT > 1 : new_item) {
+          // first tile of this chain in the item: pick the reference up (split columns: the owners of the first tile too -- the
+          // reference is the max over both halves)
           mbar_wait(&mref_full[n & 1], (n >> 1) & 1);
-          m_ref = s_mref[(n & 1) * 128 + row];
+          m_ref = s_mref[(n & 1) * NSPLIT * 128 + row];
+          if (NSPLIT > 1) m_ref = fmaxf(m_ref, s_mref[((n & 1) * NSPLIT + 1) * 128 + row]);
           ATC_ACC(d_mref);
         }
         const u64 negm2 = f2_packf(-m_ref, -m_ref);
@@ -627,11 +675,22 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         }
         // chunks of CW columns, two per iteration (registers ping-pong: the next chunk's tcgen05.ld is in flight while this one
         // is exponentiated); P is stored over score columns that have already been consumed
-        ca.ld(tS);
-        tc_wait_ld();
-        ca.fence();
+        if (!Cfg::PINGPONG) {
 #pragma unroll 1
-        for (int col = 0; col < ncols; col += 2 * CW) {
+          for (int col = 0; col < ncols; col += CW) {
+            ca.ld(tS + uint32_t(col));
+            tc_wait_ld();
+            ca.fence();
+            att_chain_chunk<DT, ATT_CHAIN_NPOLY, CW>(ca.r, la, lb, amax, sc2, negm2);
+            ca.st_lo(tS + uint32_t(col >> 1));
+          }
+        } else if (ncols > 0) {
+          ca.ld(tS);
+          tc_wait_ld();
+          ca.fence();
+        }
+#pragma unroll 1
+        for (int col = 0; Cfg::PINGPONG && col < ncols; col += 2 * CW) {
           const bool has_b = col + CW < ncols, has_a2 = col + 2 * CW < ncols;
           if (has_b) cb.ld(tS + uint32_t(col + CW));
           att_chain_chunk<DT, ATT_CHAIN_NPOLY, CW>(ca.r, la, lb, amax, sc2, negm2);
@@ -654,7 +713,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
           f2_unpack(lb, y0, y1);
           float lt = (x0 + x1) + (y0 + y1);
           if (amax > 126.0f) lt = INFINITY;          // a polynomial-path exponent left its valid range: force the exact redo
-          s_lpart[((n & 1) * Cfg::NKV_MAX + j) * 128 + row] = lt;
+          s_lpart[(((n & 1) * Cfg::NKV_MAX + j) * NSPLIT + half) * 128 + row] = lt;
         }
         tc_wait_st();
         tc_fence_before();
@@ -663,17 +722,19 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         ATC_ACC(d_exp);
       }
       // deferred epilogue of the previous item: its last tile was g - 2, i.e. this (real or virtual) tile is tile 1 of item n
-      if (j == 1 && n >= 1 && n <= n_local) epilogue(n - 1, prev_it);      // (n > n_local: a virtual tile past the virtual item)
+      if (j == epi_j && n >= 1 && n <= n_local) epilogue(n - 1);  // (n > n_local: a virtual tile past the virtual item)
       ATC_ACC(d_epi);
       j += NCH;
       while (j >= nkv) { j -= nkv; ++n; }
     }
     // exact redo of the rows flagged above (none in the common case: one ballot).  Every warp re-walks the items whose epilogue
     // it ran (tile 1 of item m + 1 belongs to chain ((m + 1) * nkv + 1) % NCH) and looks for the sentinel in its own rows.
+    // (split columns: the other half's warps may still be storing their part of a flagged row -- wait for all softmax warps)
+    if (NSPLIT > 1) asm volatile("bar.sync 1, %0;" ::"n"(SMW * 32) : "memory");
     if (__any_sync(0xffffffffu, n_bad != 0)) {
-      AtcItem x = step.first(int(blockIdx.x));
       for (int m = 0; m < n_local; ++m) {
-        if (((m + 1) * nkv + 1) % NCH == c) {
+        if (((m + 1) * nkv + 1) % NCH == c && half == 0) {
+          const AtcItem x = item_of(m);
           const int qrow = x.qt * ATT_BQ + row;
           bool flagged = false;
           if (qrow < p.N) {
@@ -687,7 +748,6 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
             att_row_exact<DT>(p, qkv_base, x.b, x.h, x.qt * ATT_BQ + (warp & 3) * 32 + r, lane);
           }
         }
-        step.next(x);
       }
     }
 #ifdef ATC_DIAG

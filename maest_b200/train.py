@@ -205,7 +205,14 @@ class MaestTrainStep(torch.autograd.Function):
             import torch.distributed as dist
             grp = None if sync in (True, "overlap") else sync
             if not overlap:
+                ev = getattr(model, "allreduce_events", None)      # bench.py: CUDA events around the exposed all-reduce
+                if ev is not None:
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    e0.record()
                 dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=grp)
+                if ev is not None:
+                    e1.record()
+                    ev.append((e0, e1))
             for w in works:
                 w.wait()
             scale /= dist.get_world_size(grp)

@@ -67,12 +67,13 @@ def child():
         ops.attention(qkv, B, N, 12, variant, save_lse=True)
         _, lse = ops.attention(qkv, B, N, 12, variant, save_lse=True)
         torch.cuda.synchronize()
-        nch, bkv = (3, 128) if variant == 3 else (4, 96)
+        nch, bkv = (4, 96) if variant == 4 else (3, 128)
+        nsm = 4 * nch * (2 if variant == 5 else 1)
         d = lse.reshape(-1)[: 148 * 512].view(148, 512).double()
         nq, nkv = (N + 127) // 128, (N + bkv - 1) // bkv
         tiles = B * 12 * nq * nkv / 148.0
         items = B * 12 * nq / 148.0
-        sm = d[:, :16 * 4 * nch].view(148, 4 * nch, 16).mean((0, 1))
+        sm = d[:, :16 * nsm].view(148, nsm, 16).mean((0, 1))
         names = ["wait_s", "wait_mref", "flush", "epilogue", "exp_to_arrive", "leader_max", "total"]
         out["tiles_per_sm"] = round(tiles)
         out["softmax_per_tile"] = {k: round(float(sm[i]) / (tiles / nch)) for i, k in enumerate(names)}
