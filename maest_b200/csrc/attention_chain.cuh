@@ -43,23 +43,33 @@ namespace mb {
 // inside its own half: PV reads k-steps 0..3 from the first half, 4..7 from the second).  Six instead of three softmax warps per
 // sub-partition: the per-tile dependency chain S -> exp -> P of a chain is half as long and the sub-partition always has a warp
 // to issue from (r02 phase clocks: with one warp per chain the softmax warps kept their sub-partition 42 % busy).
-template <int NCH_, int BKV_, int CW_, int R_, int REGS_SM_, int REGS_AUX_, int NKV_MAX_, int NSPLIT_ = 1>
+// NALT = 2: every softmax warp set owns TWO score buffers and alternates between them (tile g: set g % NCH, buffer g % (2 NCH)).
+// While a set exponentiates the tile in one buffer, PV of its previous tile and QK^T of its next one run on the tensor pipe and
+// refill the other buffer, so the set goes from tile to tile without the P -> PV -> QK^T -> S round trip (~1300 cycles per tile
+// with one buffer per set, r02 phase clocks) -- at the price of half-size tiles (twice the per-tile bookkeeping).
+template <int NCH_, int BKV_, int CW_, int R_, int REGS_SM_, int REGS_AUX_, int NKV_MAX_, int NSPLIT_ = 1, int NALT_ = 1>
 struct AtcCfgT {
   static constexpr int NCH = NCH_, BKV = BKV_, CW = CW_, R = R_, REGS_SM = REGS_SM_, REGS_AUX = REGS_AUX_, NSPLIT = NSPLIT_;
+  static constexpr int NBUF = NCH * NALT_;                 // score buffers in TMEM
+  // LEAN protocol (R == NBUF: ring slot == score buffer): the TMA producer reloads slot b when s_full[b] of the slot's previous
+  // tile has completed -- QK^T(vg - NBUF) retired, and it was only issued after PV(vg - 2 NBUF) retired, so both halves of the slot
+  // are free -- instead of waiting on kv_empty.  The issuers lose two commits per tile and walk the buffers in an unrolled loop
+  // (buffer, slot, barrier and descriptor offsets are compile-time constants; lane 0 issues, no elect).
+  static constexpr bool LEAN = R_ == NCH_ * NALT_;
   static constexpr int HW = BKV / NSPLIT;                  // score columns owned by one softmax warp
   static constexpr bool PINGPONG = NSPLIT == 1;            // two register chunks in flight (one warp per chain and quadrant needs the
                                                            // overlap; with split columns the other warps cover the tcgen05.ld latency)
   static constexpr int THREADS = (4 * NCH * NSPLIT + 4) * 32;
   static constexpr int KV_BYTES = BKV * ATT_D * 2;
   static constexpr int SLOT_BYTES = 2 * KV_BYTES;
-  static constexpr int NBAR = 2 + 2 + 2 * R + 3 * NCH + 2 + 2 + 2 + 2;
+  static constexpr int NBAR = 2 + 2 + 2 * R + 3 * NBUF + 2 + 2 + 2 + 2;
   static constexpr int OFF_KV = 2 * ATT_TILE_BYTES;
   static constexpr int OFF_BAR = OFF_KV + R * SLOT_BYTES;
   static constexpr int OFF_MREF = OFF_BAR + ((NBAR * 8 + 16 + 127) / 128) * 128;
   static constexpr int OFF_LPART = OFF_MREF + 2 * NSPLIT * 128 * 4;
   static constexpr int NKV_MAX = NKV_MAX_;      // KV tiles per item the per-tile row-sum slots are sized for
   static constexpr int SMEM_BYTES = OFF_LPART + 2 * NKV_MAX * NSPLIT * 128 * 4;
-  static_assert(NCH * BKV + 128 <= 512, "TMEM: NCH score buffers + two O accumulators");
+  static_assert(NBUF * BKV + 128 <= 512, "TMEM: score buffers + two O accumulators");
   static_assert(BKV % 32 == 0 && (CW == 32 || CW == 16), "tile / chunk shape");
   static_assert(NSPLIT == 1 || (NSPLIT == 2 && HW % 32 == 0), "column split");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
@@ -73,6 +83,8 @@ using AtcCfg4 = AtcCfgT<4, 96, 16, 6, 104, 56, 32>;      // 640 threads: 4 x 128
 #ifndef ATC_X2_CW
 #define ATC_X2_CW 16
 #endif
+using AtcCfg6 = AtcCfgT<3, 64, 32, 6, 152, 56, 32, 1, 2>;   // 3 sets x 2 buffers x 64 keys, lean protocol; 512 threads
+using AtcCfg3L = AtcCfgT<3, 128, 32, 3, 152, 56, 24>;      // 3 x 128, lean protocol
 using AtcCfg3x2 = AtcCfgT<3, 128, ATC_X2_CW, 5, ATC_X2_REGS_SM, ATC_X2_REGS_AUX, 16, 2>;   // 896 threads: 6 x 128 x 80 + 128 x 24 = 64 512 registers
 
 // ATC_LOADDIV = 2 (timing diagnostic only, results are garbage): every K / V load fetches only the first half of the tile's rows
@@ -304,10 +316,11 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
                            const void* qkv_base) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using O16 = Op16<DT>;
-  constexpr int NCH = Cfg::NCH, BKV = Cfg::BKV, CW = Cfg::CW, R = Cfg::R;
+  // NCH: score buffers (what the TMA / MMA-issuing warps step through); NSET: softmax warp sets (tile g -> set g % NSET)
+  constexpr int NCH = Cfg::NBUF, NSET = Cfg::NCH, BKV = Cfg::BKV, CW = Cfg::CW, R = Cfg::R;
   constexpr int KV_BYTES = Cfg::KV_BYTES, SLOT_BYTES = Cfg::SLOT_BYTES;
   constexpr int NSPLIT = Cfg::NSPLIT, HW = Cfg::HW, KH = HW / 16;
-  constexpr int SMW = 4 * NCH * NSPLIT;     // softmax warps
+  constexpr int SMW = 4 * NSET * NSPLIT;    // softmax warps
   uint8_t* sQ = smem;                       // [2]
   uint8_t* sKV = smem + Cfg::OFF_KV;        // [R] slots of {K tile, V tile}: the slot of "virtual tile" vg holds K(vg) and V(vg - NCH)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::OFF_BAR);
@@ -382,8 +395,40 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     int kn = 0, kj = 0, vj = 0;
     int slot = 0;
     uint32_t phase = 0;
+    if (Cfg::LEAN) {
+      uint32_t round = 0;
 #pragma unroll 1
-    for (int vg = 0; vg < n_tiles + NCH; ++vg) {
+      for (int base = 0; base < n_tiles + NCH; base += NCH, ++round) {
+#pragma unroll
+        for (int b = 0; b < NCH; ++b) {
+          const int vg = base + b;
+          if (vg >= n_tiles + NCH) break;
+          const bool has_k = vg < n_tiles, has_v = vg >= NCH;
+          ATC_T0();
+          if (has_k && kj == 0) mbar_wait(&q_empty[kn & 1], ((kn >> 1) & 1) ^ 1);
+          ATC_ACC(d_qw);
+          if (round > 0) mbar_wait(&s_full[b], (round - 1) & 1);         // QK^T(vg - NCH) retired => PV(vg - 2 NCH) retired
+          ATC_ACC(d_kw);
+          if (lane == 0) {
+            uint8_t* dst = sKV + b * SLOT_BYTES;
+            mbar_expect_tx(&kv_full[b], ((has_k ? KV_BYTES : 0) + (has_v ? KV_BYTES : 0)) / ATC_LOADDIV);
+            if (has_k) {
+              if (kj == 0) {
+                mbar_expect_tx(&q_full[kn & 1], ATT_TILE_BYTES);
+                tma_load_2d(sQ + (kn & 1) * ATT_TILE_BYTES, &tmap_q, &q_full[kn & 1], kit.h * ATT_D, kit.b * p.N + kit.qt * ATT_BQ);
+              }
+              tma_load_2d(dst, &tmap_kv, &kv_full[b], (p.H + kit.h) * ATT_D, kit.b * p.N + kj * BKV);
+            }
+            if (has_v) tma_load_2d(dst + KV_BYTES, &tmap_kv, &kv_full[b], (2 * p.H + vit.h) * ATT_D, vit.b * p.N + vj * BKV);
+          }
+          __syncwarp();
+          if (has_v && ++vj == nkv) { vj = 0; step.next(vit); }
+          if (has_k && ++kj == nkv) { kj = 0; ++kn; step.next(kit); }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int vg = 0; !Cfg::LEAN && vg < n_tiles + NCH; ++vg) {
       const bool has_k = vg < n_tiles, has_v = vg >= NCH;
       ATC_T0();
       if (has_k && kj == 0) mbar_wait(&q_empty[kn & 1], ((kn >> 1) & 1) ^ 1);
@@ -420,15 +465,70 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     // latency-bound thread) ran with the pipe idle.  Cross-warp order is by COMPLETION: QK^T(g+NCH) waits for pv_done of PV(g).
     constexpr uint32_t idesc_pv = make_idesc(DT, 128, 64, 0, 1);  // B = V, MN-major
     const uint64_t vdesc0 = make_sdesc(smem_u32(sKV + KV_BYTES), 8192, 1024);
-    unsigned d_o = 0, d_p = 0, d_kv = 0, d_pv = 0, d_cm = 0;
+    unsigned d_o = 0, d_p = 0, d_kv = 0, d_pv = 0, d_cm = 0, d_kv2 = 0;
+    (void)d_kv2;
     const long long d_start = clock64();
     (void)d_start;
     int slot = NCH % R;
     uint32_t phase = (NCH / R) & 1;
     int n = 0, j = 0, c = 0;
     uint32_t pbits = 0;                // per-chain phase parity of p_full
+    if (Cfg::LEAN) {
+      uint32_t round = 0;
 #pragma unroll 1
-    for (int g = 0; g < n_tiles; ++g) {
+      for (int base = 0; base < n_tiles; base += NCH, ++round) {
+#pragma unroll
+        for (int b = 0; b < NCH; ++b) {
+          if (base + b >= n_tiles) break;
+          ATC_T0();
+          if (j == 0) mbar_wait(&o_empty[n & 1], ((n >> 1) & 1) ^ 1);     // epilogue of item n-2 has drained this accumulator
+          ATC_ACC(d_o);
+          // P(g): completion `round` of p_full[b]; V(g) came with virtual tile g + NCH: completion round + 1 of kv_full[b]
+          const bool ok_p = mbar_try_wait(&p_full[b], round & 1), ok_kv = mbar_try_wait(&kv_full[b], (round + 1) & 1);
+          if (!ok_p) mbar_wait(&p_full[b], round & 1);
+          ATC_ACC(d_p);
+          if (!ok_kv) mbar_wait(&kv_full[b], (round + 1) & 1);
+          ATC_ACC(d_kv);
+          const bool last = (j == nkv - 1);
+          if (last && lane == 0) mbar_arrive(&lpart_full[n & 1]);         // (see the generic path below)
+          tc_fence_after();
+          // (opaque copies: without them ptxas hoists all NCH x k-step operand values out of the tile loop and spills them)
+          uint32_t tb = tmem_base;
+          uint64_t vd0 = vdesc0;
+          asm volatile("" : "+r"(tb), "+l"(vd0));
+          const uint32_t tP = tb + uint32_t(b * BKV);
+          const uint32_t tO = tb + 384u + uint32_t(n & 1) * 64u;
+          const uint64_t vd = vd0 + uint64_t(b * (SLOT_BYTES >> 4));
+          if (lane == 0) {
+#ifdef ATC_DIAG
+            const unsigned m0 = (unsigned)clock();
+#endif
+            if (!last) {
+              mma_pv<BKV / 16, KH>(tO, tP, vd, idesc_pv, uint32_t(j));
+            } else {
+              const int ksteps = nc_last >> 4;
+#pragma unroll 1
+              for (int k = 0; k < ksteps; ++k)
+                mma_ts(tO, tP + uint32_t((k / KH) * (16 * KH) + 8 * (k % KH)), vd + uint64_t(k * 128), idesc_pv, (j | k) ? 1u : 0u);
+              tc_commit(&o_full[n & 1]);
+            }
+#ifdef ATC_DIAG
+            const unsigned m1 = (unsigned)clock();
+#endif
+            tc_commit(&pv_done[b]);
+#ifdef ATC_DIAG
+            d_cm += m1 - m0;                        // "next" column: MMA issue only
+            d_kv2 += (unsigned)clock() - m1;        // "-" column 7: the commit
+#endif
+          }
+          __syncwarp();
+          ATC_ACC(d_pv);
+          if (++j == nkv) { j = 0; ++n; }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int g = 0; !Cfg::LEAN && g < n_tiles; ++g) {
       ATC_T0();
       if (j == 0) mbar_wait(&o_empty[n & 1], ((n >> 1) & 1) ^ 1);     // epilogue of item n-2 has drained this accumulator
       ATC_ACC(d_o);
@@ -472,7 +572,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
 #ifdef ATC_DIAG
     if (p.lse != nullptr && lane == 0) {
       float* d = p.lse + size_t(blockIdx.x) * 512 + 408;
-      d[0] = 0.f; d[1] = float(d_kv); d[2] = float(d_o); d[3] = float(d_p); d[4] = 0.f; d[5] = float(clock64() - d_start); d[6] = float(d_pv); d[7] = 0.f; d[8] = float(d_cm);
+      d[0] = 0.f; d[1] = float(d_kv); d[2] = float(d_o); d[3] = float(d_p); d[4] = 0.f; d[5] = float(clock64() - d_start); d[6] = float(d_pv); d[7] = float(d_kv2); d[8] = float(d_cm);
     }
 #endif
   } else if (warp == SMW + 2) {
@@ -488,8 +588,42 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     uint32_t phase = 0;
     int qn = 0, qj = 0, qc = 0;        // item, tile in item, chain of the tile
     uint32_t dbits = 0;                // per-chain phase parity of pv_done
+    if (Cfg::LEAN) {
+      uint32_t round = 0;
 #pragma unroll 1
-    for (int vg = 0; vg < n_tiles; ++vg) {
+      for (int base = 0; base < n_tiles; base += NCH, ++round) {
+#pragma unroll
+        for (int b = 0; b < NCH; ++b) {
+          if (base + b >= n_tiles) break;
+          ATC_T0();
+          if (qj == 0) mbar_wait(&q_full[qn & 1], (qn >> 1) & 1);
+          ATC_ACC(d_q);
+          // buffer b still holds P(vg - NCH) until PV(vg - NCH) retires: completion round - 1 of pv_done[b]
+          const bool ok_d = round > 0 ? mbar_try_wait(&pv_done[b], (round - 1) & 1) : true, ok_kv = mbar_try_wait(&kv_full[b], round & 1);
+          if (!ok_d) mbar_wait(&pv_done[b], (round - 1) & 1);
+          ATC_ACC(d_pvd);
+          if (!ok_kv) mbar_wait(&kv_full[b], round & 1);
+          ATC_ACC(d_kv);
+          tc_fence_after();
+          uint32_t tb = tmem_base;
+          uint64_t kd0 = kdesc0;
+          asm volatile("" : "+r"(tb), "+l"(kd0));
+          const uint64_t qd = qdesc0 + uint64_t((qn & 1) * (ATT_TILE_BYTES >> 4));
+          const uint64_t kd = kd0 + uint64_t(b * (SLOT_BYTES >> 4));
+          const bool last = (qj == nkv - 1);
+          if (lane == 0) {
+            mma_qk4(tb + uint32_t(b * BKV), qd, kd, last ? idesc_qk_last : idesc_qk);
+            tc_commit(&s_full[b]);
+            if (last) tc_commit(&q_empty[qn & 1]);
+          }
+          __syncwarp();
+          ATC_ACC(d_qk);
+          if (++qj == nkv) { qj = 0; ++qn; }
+        }
+      }
+    }
+#pragma unroll 1
+    for (int vg = 0; !Cfg::LEAN && vg < n_tiles; ++vg) {
       ATC_T0();
       if (qj == 0) mbar_wait(&q_full[qn & 1], (qn >> 1) & 1);
       ATC_ACC(d_q);
@@ -532,7 +666,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     const int c = warp / (4 * NSPLIT);
     const int half = (warp >> 2) % NSPLIT;                 // which HW-column part of the chain's tiles this warp owns
     const int row = (warp & 3) * 32 + lane;
-    const uint32_t tS = tmem_base + uint32_t(c * BKV + half * HW) + (uint32_t((warp & 3) * 32) << 16);
+    const uint32_t tS0 = tmem_base + uint32_t(half * HW) + (uint32_t((warp & 3) * 32) << 16);    // + buffer * BKV
     const float sc = p.scale_log2;
     const u64 sc2 = f2_packf(sc, sc);
     int cur_n = -1;
@@ -608,13 +742,15 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     // The epilogue of item n - 1 runs after tile epi_j of item n: the same chain as tile 1 (whose predecessor's PV is the
     // item's last), one chain round later when the item is long enough -- by then that PV has long retired (r02 clocks: at tile 1
     // the epilogue still waited ~3000 cycles for o_full).
-    const int epi_j = nkv > 1 + NCH ? 1 + NCH : 1;
+    const int epi_j = nkv > 1 + NSET ? 1 + NSET : 1;
     int n = 0, j = c;
     while (j >= nkv) { j -= nkv; ++n; }
     // NCH "virtual" tiles past the end give every chain one more pass through the item-change / epilogue logic below, so the
     // flush and the epilogue have exactly one call site each.
 #pragma unroll 1
-    for (int g = c; g < n_tiles + 2 * NCH; g += NCH) {
+    int buf = c;                       // score buffer of tile g: g % NCH
+    for (int g = c; g < n_tiles + 2 * NSET; g += NSET) {
+      const uint32_t tS = tS0 + uint32_t(buf * BKV);
       bool new_item = false;
       ATC_T0();
       if (n != cur_n) {
@@ -629,7 +765,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         // this warp's columns [half * HW, half * HW + ncols) of the tile, the first `valid` of them real keys
         const int ncols = max(0, min(HW, (last ? nc_last : BKV) - half * HW));
         const int valid = max(0, min(HW, (last ? valid_last : BKV) - half * HW));
-        mbar_wait(&s_full[c], ((g - c) / NCH) & 1);
+        mbar_wait(&s_full[buf], (g / NCH) & 1);
         ATC_ACC(d_s);
         tc_fence_after();
         AtcChunk<CW> ca, cb;
@@ -718,13 +854,15 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&p_full[c]);          // release: the row sums above and P in TMEM
+        if (lane == 0) mbar_arrive(&p_full[buf]);        // release: the row sums above and P in TMEM
         ATC_ACC(d_exp);
       }
       // deferred epilogue of the previous item: its last tile was g - 2, i.e. this (real or virtual) tile is tile 1 of item n
       if (j == epi_j && n >= 1 && n <= n_local) epilogue(n - 1);  // (n > n_local: a virtual tile past the virtual item)
       ATC_ACC(d_epi);
-      j += NCH;
+      j += NSET;
+      buf += NSET;
+      if (buf >= NCH) buf -= NCH;
       while (j >= nkv) { j -= nkv; ++n; }
     }
     // exact redo of the rows flagged above (none in the common case: one ballot).  Every warp re-walks the items whose epilogue
@@ -733,7 +871,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     if (NSPLIT > 1) asm volatile("bar.sync 1, %0;" ::"n"(SMW * 32) : "memory");
     if (__any_sync(0xffffffffu, n_bad != 0)) {
       for (int m = 0; m < n_local; ++m) {
-        if (((m + 1) * nkv + 1) % NCH == c && half == 0) {
+        if (((m + 1) * nkv + 1) % NSET == c && half == 0) {
           const AtcItem x = item_of(m);
           const int qrow = x.qt * ATT_BQ + row;
           bool flagged = false;

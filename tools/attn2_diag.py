@@ -67,7 +67,7 @@ def child():
         ops.attention(qkv, B, N, 12, variant, save_lse=True)
         _, lse = ops.attention(qkv, B, N, 12, variant, save_lse=True)
         torch.cuda.synchronize()
-        nch, bkv = (4, 96) if variant == 4 else (3, 128)
+        nch, bkv = (4, 96) if variant == 4 else (3, 64) if variant == 6 else (3, 128)
         nsm = 4 * nch * (2 if variant == 5 else 1)
         d = lse.reshape(-1)[: 148 * 512].view(148, 512).double()
         nq, nkv = (N + 127) // 128, (N + bkv - 1) // bkv
@@ -83,7 +83,7 @@ def child():
         q = d[:, 420:425].mean(0) / tiles
         out["qk_issuer_per_tile"] = dict(zip(["wait_q", "wait_kv", "wait_pv_done", "issue", "total"], [round(float(x)) for x in q]))
         m = d[:, 408:417].mean(0) / tiles
-        out["pv_issuer_per_tile"] = dict(zip(["-", "wait_kv", "wait_o_empty", "wait_p", "-", "total", "pv_issue", "-", "next"], [round(float(x)) for x in m]))
+        out["pv_issuer_per_tile"] = dict(zip(["-", "wait_kv", "wait_o_empty", "wait_p", "-", "total", "pv_issue", "commit(lean)", "next|mma(lean)"], [round(float(x)) for x in m]))
     print("ATTN2 " + json.dumps(out), flush=True)
 
 
