@@ -723,7 +723,9 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         // (the warp that owns column 0 decides, sets the sentinel and later redoes the WHOLE row)
         if (oh == 0) {
           good = good && (fabsf(__uint_as_float(v[0]) * inv_l) < INFINITY);
+#ifndef ATC_NOSOFTMAX
           if (!good && qrow < p.N) ++n_bad;   // the first output word of the row becomes the NaN sentinel 0x7fff7fff
+#endif
         }
         if (qrow < p.N) {
 #pragma unroll
@@ -765,7 +767,16 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         // this warp's columns [half * HW, half * HW + ncols) of the tile, the first `valid` of them real keys
         const int ncols = max(0, min(HW, (last ? nc_last : BKV) - half * HW));
         const int valid = max(0, min(HW, (last ? valid_last : BKV) - half * HW));
+#ifdef ATC_SLEEP_NS
+        // the scores arrive a whole P -> PV -> QK^T round trip after this chain's last arrive: sleep through most of it instead
+        // of polling (a failed try_wait + re-arm costs ~5 issue slots of the sub-partition the other chains are computing on)
+        if (!mbar_try_wait(&s_full[buf], (g / NCH) & 1)) {
+          __nanosleep(ATC_SLEEP_NS);
+          mbar_wait(&s_full[buf], (g / NCH) & 1);
+        }
+#else
         mbar_wait(&s_full[buf], (g / NCH) & 1);
+#endif
         ATC_ACC(d_s);
         tc_fence_after();
         AtcChunk<CW> ca, cb;
@@ -811,6 +822,9 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         }
         // chunks of CW columns, two per iteration (registers ping-pong: the next chunk's tcgen05.ld is in flight while this one
         // is exponentiated); P is stored over score columns that have already been consumed
+#ifdef ATC_NOSOFTMAX     // timing diagnostic: no tcgen05.ld / exp / tcgen05.st at all -- the floor set by the MMA / barrier pipeline
+        if (true) { la = f2_packf(1.f, 1.f); } else
+#endif
         if (!Cfg::PINGPONG) {
 #pragma unroll 1
           for (int col = 0; col < ncols; col += CW) {
@@ -825,6 +839,9 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
           tc_wait_ld();
           ca.fence();
         }
+#ifdef ATC_NOSOFTMAX
+        if (false)
+#endif
 #pragma unroll 1
         for (int col = 0; Cfg::PINGPONG && col < ncols; col += 2 * CW) {
           const bool has_b = col + CW < ncols, has_a2 = col + 2 * CW < ncols;

@@ -24,7 +24,7 @@ def grads(rank_seed, allreduce):
     np.random.seed(1 + rank_seed)
     loss, _ = training_forward(m, x.cuda(), y.cuda(), my_mixup(2, 0.3))
     loss.backward()
-    return torch.cat([p.grad.reshape(-1) for p in m.parameters() if p.grad is not None]).double()
+    return {n: p.grad.double().clone() for n, p in m.named_parameters() if p.grad is not None}
 
 
 def main():
@@ -33,12 +33,22 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     reduced = grads(rank, True)                       # this rank's batch, gradients averaged over the 2 ranks by train.py
     g0, g1 = grads(0, False), grads(1, False)         # both single-rank gradients, recomputed locally without communication
-    want = (g0 + g1) / 2
-    err = float((reduced - want).norm() / want.norm())
-    ok = torch.tensor([1.0 if err < 1e-5 else 0.0], device="cuda")
+    # The backward is not bit-reproducible run to run (fp32 reduce-adds in dQ and the split-K weight gradients: ~1e-7) and bf16
+    # roundings downstream amplify that by ~2.5x per block (see test_grad_allreduce_world1_equals_plain_path): tight where no
+    # amplification has happened yet, the parity tolerance elsewhere.
+    err, worst = 0.0, ""
+    good = True
+    for n, g in reduced.items():
+        want = (g0[n] + g1[n]) / 2
+        e = float((g - want).norm() / want.norm().clamp_min(1e-30))
+        tol = 1e-5 if n.startswith(("head.", "norm.", "blocks.11.")) else 1e-2
+        if e > err:
+            err, worst = e, n
+        good = good and e < tol
+    ok = torch.tensor([1.0 if good else 0.0], device="cuda")
     dist.all_reduce(ok, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print(f"rel err {err:.3e}")
+        print(f"largest rel err {err:.3e} ({worst})")
         print("DDP_GRAD_OK" if float(ok) == 1.0 else "DDP_GRAD_FAIL")
     dist.destroy_process_group()
     sys.exit(0 if float(ok) == 1.0 else 1)
