@@ -70,8 +70,12 @@ int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_str
 /* K1, dataset-file flavour.  Same STFT + mel + log compression, but the output is what the
  * reference's offline extractor stores: UN-normalised log10(1 + 1e4 mel) as float16, time-major [B, T, 96]
  * (helpers/melspectrogram_extractor.py:15-48 writes [frames, 96] float16 .mmap files; the z-norm is applied later by the
- * data module).  Note: the reference extractor runs Essentia's framing, ours is the torchaudio framing of K1 (centre = True). */
-int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, void* stream);
+ * data module).  framing 0: the torchaudio framing of K1 (reflect padding, periodic Hann, T = 1 + S/256).  framing 1: the
+ * framing of the reference's extractor, restated from Essentia's published algorithms (essentia is a third-party dependency,
+ * unpinned in pyproject.toml and absent from the reference tree): FrameCutter(frameSize 512, hopSize 256, startFromZero=false)
+ * = frames centred on sample 256 t with ZERO padding, T = ceil(S/256); Windowing(type='hann', normalized=false) = symmetric
+ * Hann; Spectrum + MelBands(slaneyMel, unit_tri, power) + log10(1 + 1e4 x) as in framing 0. */
+int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, int32_t framing, void* stream);
 
 /* Fused AdamW (+ SWA running average) over all parameters in one launch.  Replaces
  * torch.optim.AdamW as built by Module.get_optimizer (models/module.py:237-243) and the running average kept by the SWA
@@ -156,6 +160,10 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
  * (cta_group::2, W tile shared by the two SMs of a TPC), 2 = per-shape choice (default).  Process-wide tuning switch;
  * results are identical. */
 int32_t maest_set_gemm_mode(int32_t pair_mode);
+
+/* Host-side TMA descriptor cache (api.cu make_tmap): lookups served from the calling thread's cache / descriptors encoded
+ * through cuTensorMapEncodeTiled since the library was loaded.  Diagnostic only; either pointer may be NULL. */
+int32_t maest_tmap_cache_stats(uint64_t* hits, uint64_t* misses);
 
 /* LayerNorm folding, weight side (once per weight version): wg[n] = sum_k gamma[k] W[n,k], bf[n] = bias[n] + sum_k beta[k] W[n,k]
  * from the 16-bit operand copy w16 [N, K] that the GEMM multiplies.  Replaces nothing by itself: it moves norm1 / norm2

@@ -16,7 +16,7 @@ c_void_p, c_int32, c_int64, c_size_t, c_float = C.c_void_p, C.c_int32, C.c_int64
 F16, BF16, F32 = 0, 1, 2
 EPI_STORE16, EPI_GELU16, EPI_RESID32, EPI_STORE32, EPI_GELUBWD16, EPI_ATOMIC32 = 0, 1, 2, 3, 4, 5
 EPI_STORE16_LN, EPI_GELU16_LN, EPI_RESID32_LN = 7, 8, 9
-ABI_VERSION = 7
+ABI_VERSION = 8
 HEAD_MEAN, HEAD_SEPARATED = 0, 1
 
 
@@ -31,7 +31,7 @@ SIGNATURES = {
     "maest_abi_version": (c_int32, []),
     "maest_init": (c_int32, [c_int32]),
     "maest_logmel_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
-    "maest_logmel_raw16_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p]),
+    "maest_logmel_raw16_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_int32, c_void_p]),
     "maest_mel_ingest_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_float, c_float, c_void_p, c_void_p]),
     "maest_adamw_step": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_float, c_float, c_float, c_float, c_int32, c_float, c_float, c_void_p]),
     "maest_swa_fold": (c_int32, [c_void_p, c_void_p, c_int32, c_float, c_void_p]),
@@ -51,6 +51,7 @@ SIGNATURES = {
                                       c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "maest_ln_finalize": (c_int32, [c_void_p, c_int32, c_int32, c_float, c_void_p, c_void_p]),
     "maest_set_gemm_mode": (c_int32, [c_int32]),
+    "maest_tmap_cache_stats": (c_int32, [c_void_p, c_void_p]),
     "maest_attention_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "maest_attention_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "maest_mixup_fwd": (c_int32, [c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_int64, c_void_p]),

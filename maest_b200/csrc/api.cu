@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/maest_b200.h"
@@ -56,7 +57,40 @@ int cur_device() {
 
 // 2-D tensor map over a row-major 16-bit matrix [rows, cols] (row stride ld elements); box = [box_rows, 64 cols]
 // (128-byte inner extent), SWIZZLE_128B, out-of-bounds elements read as zero.
+// A tensor map is a pure function of (pointer, dtype, shape, stride, box): the activations live in caller-owned buffers that
+// are reused step after step and the weights never move, so the ~200 encodes per forward step collapse into lookups of a small
+// per-thread direct-mapped cache (cuTensorMapEncodeTiled costs a microsecond or two on the host -- invisible at batch 64,
+// the dominant host cost of a one-clip predict_labels call).
+struct TmapKey {
+  const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows; int32_t dt;
+  bool operator==(const TmapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && dt == o.dt;
+  }
+};
+struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
+constexpr int TMAP_CACHE_SLOTS = 1024;
+thread_local TmapSlot g_tmap_cache[TMAP_CACHE_SLOTS];
+uint64_t g_tmap_hits = 0, g_tmap_misses = 0;
+
+int make_tmap_uncached(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+
 int make_tmap(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  const TmapKey key{ptr, rows, cols, ld, box_rows, dt};
+  uint64_t h = reinterpret_cast<uintptr_t>(ptr) >> 4;
+  h = (h ^ (h >> 17) ^ (rows * 0x9E3779B97F4A7C15ull) ^ (cols << 7) ^ (ld << 13) ^ (uint64_t(box_rows) << 29) ^ uint64_t(dt)) * 0xD6E8FEB86659FD93ull;
+  TmapSlot& slot = g_tmap_cache[(h >> 40) % TMAP_CACHE_SLOTS];
+  static const bool enabled = [] { const char* e = getenv("MAEST_TMAP_CACHE"); return !(e && e[0] == '0'); }();   // A/B switch
+  if (enabled && slot.valid && slot.key == key) {
+    *m = slot.map;
+    ++g_tmap_hits;
+    return 0;
+  }
+  const int r = make_tmap_uncached(m, ptr, dt, rows, cols, ld, box_rows);
+  if (r == 0) { slot.key = key; slot.map = *m; slot.valid = true; ++g_tmap_misses; }
+  return r;
+}
+
+int make_tmap_uncached(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   if (!g_encode) return fail(-3, "maest_init() was not called");
   if ((reinterpret_cast<uintptr_t>(ptr) & 15) || (ld * 2) % 16) return fail(-4, "operand not 16-byte aligned (ptr %p ld %llu)", ptr, (unsigned long long)ld);
   cuuint64_t dims[2] = {cols, rows};
@@ -208,7 +242,13 @@ int init_dt() {
 extern "C" {
 
 const char* maest_last_error(void) { return g_err; }
-int32_t maest_abi_version(void) { return 7; }
+int32_t maest_abi_version(void) { return 8; }
+
+int32_t maest_tmap_cache_stats(uint64_t* hits, uint64_t* misses) {
+  if (hits) *hits = g_tmap_hits;
+  if (misses) *misses = g_tmap_misses;
+  return 0;
+}
 
 int32_t maest_init(int32_t device) {
   if (device < 0 || device >= 64) return fail(-1, "bad device %d", device);
@@ -237,13 +277,16 @@ int32_t maest_init(int32_t device) {
   return 0;
 }
 
-static int32_t logmel_launch(const float* wav, int32_t B, int32_t S, int64_t wav_stride, float* mel, void* raw_tm16, void* stream) {
+static int32_t logmel_launch(const float* wav, int32_t B, int32_t S, int64_t wav_stride, float* mel, void* raw_tm16, void* stream,
+                             int32_t essentia_framing = 0) {
   const int dev = cur_device();
   if (!g_inited[dev]) return fail(-3, "maest_init() was not called for device %d", dev);
   if (B <= 0) return 0;
   if (S <= LM_HOP) return fail(-1, "waveform of %d samples is too short for reflect padding (need > 256)", S);
   LogMelParams p;
-  p.wav = wav; p.wav_stride = wav_stride; p.B = B; p.S = S; p.T = 1 + S / LM_HOP; p.mel = mel;
+  p.wav = wav; p.wav_stride = wav_stride; p.B = B; p.S = S; p.mel = mel;
+  p.T = essentia_framing ? (S + LM_HOP - 1) / LM_HOP : 1 + S / LM_HOP;
+  p.essentia_framing = essentia_framing ? 1 : 0;
   p.raw_tm16 = reinterpret_cast<__half*>(raw_tm16);
   p.tables = g_lm_tables[dev];
   dim3 grid((p.T + LM_FRAMES - 1) / LM_FRAMES, B);
@@ -257,9 +300,10 @@ int32_t maest_logmel_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_str
   return logmel_launch(wav, B, S, wav_stride, mel, nullptr, stream);
 }
 
-int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, void* stream) {
+int32_t maest_logmel_raw16_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, void* raw_tm16, int32_t framing, void* stream) {
   if (!raw_tm16) return fail(-1, "logmel_raw16: output is NULL");
-  return logmel_launch(wav, B, S, wav_stride, nullptr, raw_tm16, stream);
+  if (framing != 0 && framing != 1) return fail(-1, "logmel_raw16: framing must be 0 (torchaudio) or 1 (essentia), got %d", framing);
+  return logmel_launch(wav, B, S, wav_stride, nullptr, raw_tm16, stream, framing);
 }
 
 int32_t maest_adamw_step(const void* tensor_table, const void* chunk_table, int32_t n_chunks, float lr, float beta1, float beta2,

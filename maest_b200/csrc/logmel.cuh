@@ -11,8 +11,8 @@
 // is applied in its sparse triangular form (<= 15 bins per band, 502 non-zeros), and results are staged
 // in smem so that global stores are contiguous along time.
 //
-// The per-thread phase functions below are __host__ __device__: tests/test_logmel_host_emulation.py
-// compiles this header with g++ (MB_HOST_EMULATION) and replays the exact index arithmetic on the CPU.
+// The per-thread phase functions below are __host__ __device__: tests/test_api_cpu.py::test_logmel_kernel_host_emulation
+// compiles this header with g++ (tests/logmel_host_emu.cpp, MB_HOST_EMULATION) and replays the exact index arithmetic on the CPU.
 #pragma once
 #ifndef MB_HOST_EMULATION
 #include "common.cuh"
@@ -40,10 +40,11 @@ constexpr int LM_MAX_TAPS = 16;
 // tables shared by all CTAs (built on the host in double precision)
 struct LogMelTables {
   float2 tw[LM_NFFT];        // W512^j = exp(-2 pi i j / 512)
-  float hann[LM_NFFT];       // periodic Hann
+  float hann[LM_NFFT];       // periodic Hann (torchaudio framing); replaced in smem by hann_sym for the Essentia framing
   int band_start[LM_NMEL];   // first FFT bin with non-zero weight
   int band_len[LM_NMEL];     // number of bins (<= LM_MAX_TAPS)
   float band_w[LM_NMEL * LM_MAX_TAPS];
+  float hann_sym[LM_NFFT];   // symmetric Hann 0.5 - 0.5 cos(2 pi j / 511): Essentia's Windowing(type='hann')
 };
 
 // per-group scratch (floats): bufA re/im [8*72], bufB re/im [8*65]
@@ -186,6 +187,10 @@ struct LogMelParams {
   __half* raw_tm16;   // [B, T, 96] un-normalised log10(1 + 1e4 mel) as fp16, time-major: the layout of the reference's
                       // .mmap training files (helpers/melspectrogram_extractor.py:45-47), or null
   const LogMelTables* tables;
+  int essentia_framing;   // 0: torchaudio (reflect padding, periodic Hann, T = 1 + S / 256) -- the model's front-end;
+                          // 1: Essentia FrameCutter(startFromZero=false) + Windowing('hann', normalized=false): frames centred on
+                          //    256 t, ZERO padding outside the signal, symmetric Hann, T = ceil(S / 256) -- what the offline
+                          //    extractor of the reference runs (helpers/melspectrogram_extractor.py:15-30)
 };
 
 constexpr int LM_THREADS = 64 * LM_GROUPS;
@@ -215,9 +220,20 @@ __global__ void __launch_bounds__(LM_THREADS, 2) logmel_kernel(const LogMelParam
     const float* x = p.wav + long(b) * p.wav_stride;
     const int base = LM_HOP * (t0 - 1);
     const int need = (nfr + 1) * LM_HOP;
-    for (int i = tid; i < need; i += LM_THREADS) seg[i] = __ldg(x + lm_reflect(base + i, p.S));
+    if (p.essentia_framing) {
+      for (int i = tid; i < need; i += LM_THREADS) {
+        const int s = base + i;
+        seg[i] = (s >= 0 && s < p.S) ? __ldg(x + s) : 0.f;
+      }
+    } else {
+      for (int i = tid; i < need; i += LM_THREADS) seg[i] = __ldg(x + lm_reflect(base + i, p.S));
+    }
   }
   __syncthreads();
+  if (p.essentia_framing) {
+    for (int i = tid; i < LM_NFFT; i += LM_THREADS) tb.hann[i] = tb.hann_sym[i];
+    __syncthreads();
+  }
 
   const int g = tid >> 6, gt = tid & 63;
   float* bufA_re = scratch + g * LM_GROUP_FLOATS;

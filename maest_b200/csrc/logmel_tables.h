@@ -27,6 +27,7 @@ inline int build_logmel_tables(LogMelTables* tb) {
     tb->tw[j].x = (float)cos(a);
     tb->tw[j].y = (float)sin(a);
     tb->hann[j] = (float)(0.5 - 0.5 * cos(2.0 * PI * j / LM_NFFT));
+    tb->hann_sym[j] = (float)(0.5 - 0.5 * cos(2.0 * PI * j / (LM_NFFT - 1)));
   }
   const int n_freqs = LM_NFFT / 2 + 1;
   double f_pts[LM_NMEL + 2];

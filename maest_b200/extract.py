@@ -2,11 +2,13 @@
 file format -- raw float16 `[frames, 96]` `.mmap`, un-normalised log10(1 + 1e4 mel), centre-trimmed to `max_duration`
 (helpers/melspectrogram_extractor.py:15-48, datasets/mtt/preprocess.py:44-64).
 
-    python -m maest_b200.extract audio.wav melbands.mmap [--force] [--max-duration 300]
+    python -m maest_b200.extract audio.wav melbands.mmap [--force] [--max-duration 300] [--framing essentia|torchaudio]
 
-The reference runs Essentia (`TensorflowInputMusiCNN`-style framing, not installed here); this tool runs the model's own
-front-end (K1: torchaudio framing, centre = True), so a file of S samples yields 1 + S // 256 frames.  Audio decoding is
-limited to what the image has: 16 kHz mono PCM `.wav` (stdlib `wave`) or `.npy` float arrays.
+The reference runs Essentia (not installed here, not vendored by the reference).  `--framing essentia` (default) reproduces its
+framing as published -- centred frames with zero padding, symmetric Hann, ceil(S / 256) frames, so a 30 s file gives the 1875
+frames the discogs models were trained on; `--framing torchaudio` runs the model's own front-end (reflect padding, periodic
+Hann, 1 + S // 256 frames).  Audio decoding is limited to what the image has: 16 kHz mono PCM `.wav` (stdlib `wave`) or `.npy`
+float arrays.
 """
 from __future__ import annotations
 
@@ -49,16 +51,16 @@ def trim_bounds(n_frames: int, max_duration: float):
     return 0, n_frames
 
 
-def melspectrogram_extractor(waveform: torch.Tensor) -> torch.Tensor:
+def melspectrogram_extractor(waveform: torch.Tensor, framing: str = "essentia") -> torch.Tensor:
     """[S] or [B, S] waveform on the GPU -> float16 [T, 96] / [B, T, 96] (time-major, un-normalised)."""
-    return ops.logmel_raw16(waveform)
+    return ops.logmel_raw16(waveform, framing=framing)
 
 
-def main(audio_file, melbands_file, force=False, max_duration=300, device="cuda"):
+def main(audio_file, melbands_file, force=False, max_duration=300, device="cuda", framing="essentia"):
     if os.path.exists(melbands_file) and not force:
         return None
     x = torch.from_numpy(load_audio(audio_file)).to(device)
-    mel = melspectrogram_extractor(x)
+    mel = melspectrogram_extractor(x, framing)
     a, b = trim_bounds(mel.shape[0], max_duration)
     mel = mel[a:b].cpu().numpy()
     Path(melbands_file).parent.mkdir(parents=True, exist_ok=True)
@@ -74,4 +76,5 @@ if __name__ == "__main__":
     ap.add_argument("melbands_file", type=str)
     ap.add_argument("--force", "-f", action="store_true")
     ap.add_argument("--max-duration", type=float, default=300)
+    ap.add_argument("--framing", default="essentia", choices=["essentia", "torchaudio"])
     main(**vars(ap.parse_args()))

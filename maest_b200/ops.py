@@ -70,9 +70,14 @@ def logmel(wav: torch.Tensor) -> torch.Tensor:
     return mel[0] if squeeze else mel
 
 
-def logmel_raw16(wav: torch.Tensor) -> torch.Tensor:
+def logmel_raw16(wav: torch.Tensor, framing: str = "torchaudio") -> torch.Tensor:
     """[B, S] fp32 CUDA waveform -> [B, T, 96] fp16, un-normalised log10(1 + 1e4 mel), time-major: the layout of the
-    reference's .mmap training files (helpers/melspectrogram_extractor.py)."""
+    reference's .mmap training files (helpers/melspectrogram_extractor.py).  framing "torchaudio": the model's own front-end
+    (reflect padding, periodic Hann, T = 1 + S // 256); "essentia": the framing of the reference's offline extractor
+    (FrameCutter centred frames with zero padding, symmetric Hann, T = ceil(S / 256))."""
+    if framing not in ("torchaudio", "essentia"):
+        raise ValueError(f"framing must be 'torchaudio' or 'essentia', got {framing!r}")
+    ess = framing == "essentia"
     _need_cuda(wav)
     w = wav.reshape(1, -1) if wav.dim() == 1 else wav
     if w.dtype != torch.float32:
@@ -80,10 +85,10 @@ def logmel_raw16(wav: torch.Tensor) -> torch.Tensor:
     if w.stride(-1) != 1:
         w = w.contiguous()
     B, S = w.shape
-    out = torch.empty((B, 1 + S // 256, 96), device=w.device, dtype=torch.float16)
+    out = torch.empty((B, (S + 255) // 256 if ess else 1 + S // 256, 96), device=w.device, dtype=torch.float16)
     with torch.cuda.device(w.device):
         lib = _lib_for(w)
-        _lib.check(lib.maest_logmel_raw16_fwd(w.data_ptr(), B, S, w.stride(0), out.data_ptr(), _stream()), "logmel_raw16")
+        _lib.check(lib.maest_logmel_raw16_fwd(w.data_ptr(), B, S, w.stride(0), out.data_ptr(), int(ess), _stream()), "logmel_raw16")
     return out[0] if wav.dim() == 1 else out
 
 

@@ -124,6 +124,37 @@ def logmel(wave: torch.Tensor, dtype=torch.float32, normalise: bool = True) -> t
     return out.transpose(1, 2).reshape(*lead, N_MELS, T)
 
 
+def hann_symmetric(dtype=torch.float64) -> torch.Tensor:
+    n = torch.arange(N_FFT, dtype=torch.float64)
+    return (0.5 - 0.5 * torch.cos(2.0 * math.pi * n / (N_FFT - 1))).to(dtype)
+
+
+def logmel_essentia_framing(wave: torch.Tensor, dtype=torch.float64) -> torch.Tensor:
+    """[..., S] waveform -> [..., T, 96] UN-normalised log10(1 + 1e4 mel), T = ceil(S / 256): the dataset-file flavour with the
+    framing of the reference's offline extractor (helpers/melspectrogram_extractor.py:15-30 -> essentia.pytools.extractors.
+    melspectrogram).  PARITY UNPINNED: Essentia is a third-party dependency (unpinned in pyproject.toml:17-29), neither installed
+    here nor vendored under /root/reference, and the reference holds no vectors produced by it; this restates its published
+    algorithms: FrameCutter(frameSize=512, hopSize=256, startFromZero=False): frame t covers samples [256 t - 256, 256 t + 256)
+    with zeros outside the signal, frames while the centre 256 t lies inside it; Windowing(type='hann', normalized=False):
+    symmetric Hann (zero-phase rotation does not change magnitudes); Spectrum -> |rfft|; MelBands(96 bands, 0-8000 Hz, slaneyMel
+    warping, 'unit_tri' normalisation, type='power'): the same triangles as torchaudio's slaney filterbank applied to |X|^2;
+    'shift_scale_log': log10(1 + 1e4 x).  Interior frames differ from `logmel(normalise=False)` only by the window
+    (periodic vs symmetric Hann); the reference's authors quote 1e-3 relative / 1e-3 absolute between the two
+    (models/helpers/melspectrogram.py:8-10) and tests/test_oracle_golden.py::test_essentia_framing_gap measures it here."""
+    lead = wave.shape[:-1]
+    x = wave.reshape(-1, wave.shape[-1]).to(dtype)
+    S = x.shape[-1]
+    T = (S + HOP - 1) // HOP
+    pad = N_FFT // 2
+    need = (T - 1) * HOP + N_FFT
+    xp = torch.cat([x.new_zeros(x.shape[0], pad), x, x.new_zeros(x.shape[0], max(0, need - pad - S))], dim=-1)
+    frames = xp.unfold(-1, N_FFT, HOP)[:, :T, :] * hann_symmetric(dtype)
+    spec = torch.fft.rfft(frames, dim=-1)
+    power = spec.real ** 2 + spec.imag ** 2
+    mel = power @ mel_filterbank(dtype)
+    return torch.log10(1.0 + mel * 10000.0).reshape(*lead, T, N_MELS)
+
+
 # ----------------------------------------------------------------------------------------------
 # tokens
 # ----------------------------------------------------------------------------------------------

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
     for name in declared:
         assert getattr(lib, name) is not None
-    assert lib.maest_abi_version() == _lib.ABI_VERSION == 7
+    assert lib.maest_abi_version() == _lib.ABI_VERSION == 8
     assert lib.maest_encoder_workspace_bytes(1000) > 1000 * 13824
     assert lib.maest_patch_workspace_bytes(2, 558) >= 2 * 558 * 512 + 558 * 3072
 
@@ -179,3 +179,28 @@ def test_input_f_other_than_96_is_refused():
     from maest_b200 import get_maest
     with pytest.raises(NotImplementedError):
         get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, input_f=128)
+
+
+def test_checkpoint_argument_follows_the_reference(tmp_path):
+    """get_maest(checkpoint=...) (models/maest.py:1553-1567): a Lightning checkpoint's "state_dict", `net_swa.` prefix stripped when
+    checkpoint_swa_weigts (sic) is set -- and, as in the reference, NOTHING stripped when it is not (`replace("", "")`), so plain
+    `net.*` keys then load nothing under strict=False; checkpoint_discard_head drops every key containing "head"."""
+    import torch
+    from maest_b200 import get_maest, synth
+    sd = synth.synth_state_dict(62, 400, seed=3)
+    ck = {"state_dict": {**{"net_swa." + k: v for k, v in sd.items()}, **{"net." + k: v + 1 for k, v in sd.items()}}}
+    path = str(tmp_path / "last.ckpt")
+    torch.save(ck, path)
+    base = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False)
+    m = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, checkpoint=path)
+    got = m.state_dict()
+    for k in ("blocks.3.attn.qkv.weight", "head.1.weight", "time_new_pos_embed", "cls_token"):
+        assert torch.equal(got[k], sd[k]), k
+    m2 = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, checkpoint=path, checkpoint_discard_head=True)
+    got2 = m2.state_dict()
+    assert torch.equal(got2["blocks.3.attn.qkv.weight"], sd["blocks.3.attn.qkv.weight"])
+    assert not torch.equal(got2["head.1.weight"], sd["head.1.weight"])
+    torch.manual_seed(0)
+    m3 = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, checkpoint=path, checkpoint_swa_weigts=False)
+    assert not torch.equal(m3.state_dict()["blocks.3.attn.qkv.weight"], sd["blocks.3.attn.qkv.weight"])
+    assert set(got) == set(base.state_dict())

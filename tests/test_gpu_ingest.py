@@ -78,9 +78,27 @@ def test_raw_logmel_file_format(tmp_path):
     wav = str(tmp_path / "a.npy")
     np.save(wav, x[0].numpy())
     dst = str(tmp_path / "out" / "a.mmap")
-    shape = extract.main(wav, dst, max_duration=2)
+    shape = extract.main(wav, dst, max_duration=2, framing="torchaudio")
     assert shape == (124, 96)                                           # int(2 * 16000 / 256) = 125 -> 2 * (125 // 2) frames
     disk = np.memmap(dst, dtype="float16", mode="r", shape=shape)
     a, b = IO.trim_bounds(got.shape[1], 2)
     assert np.array_equal(np.asarray(disk).view(np.uint16), got[0, a:b].numpy().view(np.uint16))
     assert extract.main(wav, dst, max_duration=2) is None              # exists, not forced
+
+
+def test_raw_logmel_essentia_framing(tmp_path):
+    """framing="essentia" (the reference's offline extractor, helpers/melspectrogram_extractor.py:15-30): zero-padded centred
+    frames, symmetric Hann, ceil(S / 256) frames -- against the float64 restatement of Essentia's published algorithms."""
+    from maest_b200 import extract, ops, synth
+    for S in (48000, 480000, 4999, 257):
+        x = torch.cat([synth.wave_a(1, S), synth.wave_b(S).reshape(1, -1)], 0)
+        got = ops.logmel_raw16(x.cuda(), framing="essentia").cpu()
+        ref = O.logmel_essentia_framing(x, dtype=torch.float64)
+        assert got.shape == ref.shape == (2, (S + 255) // 256, 96)
+        ulp = (got.view(torch.int16).int() - ref.to(torch.float16).view(torch.int16).int()).abs()
+        assert int(ulp.max()) <= 1 and float((ulp == 0).float().mean()) > 0.99, (S, int(ulp.max()))
+    wav = str(tmp_path / "b.npy")
+    np.save(wav, synth.wave_a(1, 480000)[0].numpy())
+    assert extract.main(wav, str(tmp_path / "b.mmap")) == (1875, 96)   # a 30 s file -> the 1875 frames of the discogs models
+    with pytest.raises(ValueError):
+        ops.logmel_raw16(x.cuda(), framing="librosa")
