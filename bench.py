@@ -435,7 +435,7 @@ def main():
     ap.add_argument("--arch", default="discogs-maest-30s-pw-129e")
     ap.add_argument("--batch", type=int, default=64, help="clips per GPU per step")
     ap.add_argument("--op-dtype", default="fp16", choices=["fp16", "bf16"])
-    ap.add_argument("--attn-variant", type=int, default=3)
+    ap.add_argument("--attn-variant", type=int, default=8)
     ap.add_argument("--fuse-ln", action="store_true", help="fold the LayerNorms into the GEMM epilogues around them (A/B; default off)")
     ap.add_argument("--ref-clips", type=int, default=2, help="--impl reference: clips per step (bounded CPU sample)")
     ap.add_argument("--cpu-baseline-clips", type=int, default=4)
@@ -615,7 +615,7 @@ def main():
                 with open(afiles[-1]) as tf:
                     a_traffic = json.load(tf).get("dram_bytes_per_launch")
             kname = {0: "attention_fwd_spec_kernel", 3: "attention_fwd_chain_kernel<3 x 128>", 4: "attention_fwd_chain_kernel<4 x 96>",
-                     5: "attention_fwd_chain_kernel<3 x 128, split columns>"}.get(model_attn_variant, f"attention variant {model_attn_variant}")
+                     5: "attention_fwd_chain_kernel<3 x 128, split columns>", 8: "attention_fwd_chain_kernel<3 x 128 + epilogue warpgroup>"}.get(model_attn_variant, f"attention variant {model_attn_variant}")
             line["roofline"] = dict(bound="tensor", kernel=f"{kname} (12 launches per step)", achieved=a_tf,
                                     peak=peaks["bf16_tflops_sustained"], unit="TFLOP/s", frac=a_tf / peaks["bf16_tflops_sustained"],
                                     traffic=a_traffic, algorithmic_flops_per_launch=B * fl["attention"] / DEPTH,

@@ -232,8 +232,9 @@ int init_dt() {
   if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg3>, AtcCfg3::SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg4>, AtcCfg4::SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg3x2>, AtcCfg3x2::SMEM_BYTES))) return r;
-  if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg6>, AtcCfg6::SMEM_BYTES))) return r;
   if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg3L>, AtcCfg3L::SMEM_BYTES))) return r;
+  if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg3E>, AtcCfg3E::SMEM_BYTES))) return r;
+  if ((r = set_smem(attention_fwd_chain_kernel<DT, AtcCfg3EH>, AtcCfg3EH::SMEM_BYTES))) return r;
   return 0;
 }
 
@@ -490,10 +491,11 @@ int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, i
     case 3:    // chains kernel, 3 chains x 128 keys (attention_chain.cuh); needs >= 2 KV tiles per item
     case 4:    // chains kernel, 4 chains x 96 keys
     case 5:    // chains kernel, 3 chains x 128 keys, two softmax warps per (chain, lane quadrant) splitting the columns
-    case 6:    // chains kernel, 3 softmax sets x 2 alternating buffers x 64 keys
-    case 7: {  // chains kernel, 3 x 128, lean protocol
-      const int bkv = variant == 4 ? AtcCfg4::BKV : variant == 6 ? AtcCfg6::BKV : AtcCfg3::BKV;
-      const int nkv_max = variant == 4 ? AtcCfg4::NKV_MAX : variant == 5 ? AtcCfg3x2::NKV_MAX : variant == 6 ? AtcCfg6::NKV_MAX : AtcCfg3::NKV_MAX;
+    case 7:    // chains kernel, 3 x 128, lean protocol
+    case 8:    // chains kernel, 3 x 128, dedicated epilogue warpgroup
+    case 9: {  // ... + PV starts on the first half of P
+      const int bkv = variant == 4 ? AtcCfg4::BKV : AtcCfg3::BKV;
+      const int nkv_max = variant == 4 ? AtcCfg4::NKV_MAX : variant == 5 ? AtcCfg3x2::NKV_MAX : AtcCfg3::NKV_MAX;
       if (N <= bkv || (N + bkv - 1) / bkv > nkv_max) return maest_attention_fwd(qkv, out, lse, B, N, H, op_dtype, 0, stream);
       const int items = B * H * ((N + ATT_BQ - 1) / ATT_BQ);
       const int sms = g_num_sms[cur_device()];
@@ -503,12 +505,15 @@ int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, i
       if (variant == 3) {
         if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg3><<<g, AtcCfg3::THREADS, AtcCfg3::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
         else attention_fwd_chain_kernel<DT_F16, AtcCfg3><<<g, AtcCfg3::THREADS, AtcCfg3::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+      } else if (variant == 9) {
+        if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg3EH><<<g, AtcCfg3EH::THREADS, AtcCfg3EH::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+        else attention_fwd_chain_kernel<DT_F16, AtcCfg3EH><<<g, AtcCfg3EH::THREADS, AtcCfg3EH::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+      } else if (variant == 8) {
+        if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg3E><<<g, AtcCfg3E::THREADS, AtcCfg3E::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
+        else attention_fwd_chain_kernel<DT_F16, AtcCfg3E><<<g, AtcCfg3E::THREADS, AtcCfg3E::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
       } else if (variant == 7) {
         if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg3L><<<g, AtcCfg3L::THREADS, AtcCfg3L::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
         else attention_fwd_chain_kernel<DT_F16, AtcCfg3L><<<g, AtcCfg3L::THREADS, AtcCfg3L::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
-      } else if (variant == 6) {
-        if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg6><<<g, AtcCfg6::THREADS, AtcCfg6::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
-        else attention_fwd_chain_kernel<DT_F16, AtcCfg6><<<g, AtcCfg6::THREADS, AtcCfg6::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
       } else if (variant == 5) {
         if (bf) attention_fwd_chain_kernel<DT_BF16, AtcCfg3x2><<<g, AtcCfg3x2::THREADS, AtcCfg3x2::SMEM_BYTES, st>>>(tq, tkv, p, qkv);
         else attention_fwd_chain_kernel<DT_F16, AtcCfg3x2><<<g, AtcCfg3x2::THREADS, AtcCfg3x2::SMEM_BYTES, st>>>(tq, tkv, p, qkv);

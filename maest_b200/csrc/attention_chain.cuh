@@ -47,8 +47,19 @@ namespace mb {
 // While a set exponentiates the tile in one buffer, PV of its previous tile and QK^T of its next one run on the tensor pipe and
 // refill the other buffer, so the set goes from tile to tile without the P -> PV -> QK^T -> S round trip (~1300 cycles per tile
 // with one buffer per set, r02 phase clocks) -- at the price of half-size tiles (twice the per-tile bookkeeping).
-template <int NCH_, int BKV_, int CW_, int R_, int REGS_SM_, int REGS_AUX_, int NKV_MAX_, int NSPLIT_ = 1, int NALT_ = 1>
+// REGS_EPI > 0: a dedicated EPILOGUE warpgroup (4 more warps) turns every finished item's O / l into the 16-bit output.  With the
+// epilogue inside the softmax chains, one chain disappeared for ~5000 cycles per item (r02 clocks: 370 cycles per tile and
+// chain) and, because PV / QK^T are issued in tile order, the other two chains ran into its missing P a tile or two later.
+// PHALF: the softmax warps also arrive on p_half once the packed P of the first half of the tile's keys is in TMEM (three
+// quarters through the tile: the tcgen05.wait::st sits behind the third chunk's arithmetic, where it is free), and the PV issuer
+// starts the first BKV/32 k-steps then.  PV is ISSUE-bound (one tcgen05.mma per ~53 cycles from one thread, r02_ubench_mma_issue),
+// so half of its 426 issue cycles leave the P -> PV -> QK^T -> S round trip.
+template <int NCH_, int BKV_, int CW_, int R_, int REGS_SM_, int REGS_AUX_, int NKV_MAX_, int NSPLIT_ = 1, int NALT_ = 1, int REGS_EPI_ = 0,
+          bool PHALF_ = false>
 struct AtcCfgT {
+  static constexpr bool PHALF = PHALF_;
+  static constexpr bool EPIWG = REGS_EPI_ > 0;
+  static constexpr int REGS_EPI = REGS_EPI_;
   static constexpr int NCH = NCH_, BKV = BKV_, CW = CW_, R = R_, REGS_SM = REGS_SM_, REGS_AUX = REGS_AUX_, NSPLIT = NSPLIT_;
   static constexpr int NBUF = NCH * NALT_;                 // score buffers in TMEM
   // LEAN protocol (R == NBUF: ring slot == score buffer): the TMA producer reloads slot b when s_full[b] of the slot's previous
@@ -59,10 +70,10 @@ struct AtcCfgT {
   static constexpr int HW = BKV / NSPLIT;                  // score columns owned by one softmax warp
   static constexpr bool PINGPONG = NSPLIT == 1;            // two register chunks in flight (one warp per chain and quadrant needs the
                                                            // overlap; with split columns the other warps cover the tcgen05.ld latency)
-  static constexpr int THREADS = (4 * NCH * NSPLIT + 4) * 32;
+  static constexpr int THREADS = (4 * NCH * NSPLIT + 4 + (EPIWG ? 4 : 0)) * 32;
   static constexpr int KV_BYTES = BKV * ATT_D * 2;
   static constexpr int SLOT_BYTES = 2 * KV_BYTES;
-  static constexpr int NBAR = 2 + 2 + 2 * R + 3 * NBUF + 2 + 2 + 2 + 2;
+  static constexpr int NBAR = 2 + 2 + 2 * R + 4 * NBUF + 2 + 2 + 2 + 2;
   static constexpr int OFF_KV = 2 * ATT_TILE_BYTES;
   static constexpr int OFF_BAR = OFF_KV + R * SLOT_BYTES;
   static constexpr int OFF_MREF = OFF_BAR + ((NBAR * 8 + 16 + 127) / 128) * 128;
@@ -73,6 +84,7 @@ struct AtcCfgT {
   static_assert(BKV % 32 == 0 && (CW == 32 || CW == 16), "tile / chunk shape");
   static_assert(NSPLIT == 1 || (NSPLIT == 2 && HW % 32 == 0), "column split");
   static_assert(SMEM_BYTES <= 227 * 1024, "shared memory");
+  static_assert(!PHALF || (NSPLIT == 1 && CW == 32 && BKV == 128 && R_ != NCH_ * NALT_), "PHALF: generic ring, 4 chunks of 32 per tile");
 };
 using AtcCfg3 = AtcCfgT<3, 128, 32, 5, 152, 56, 24>;     // 512 threads: 3 x 128 x 152 + 128 x 56 = 65 536 registers
 using AtcCfg4 = AtcCfgT<4, 96, 16, 6, 104, 56, 32>;      // 640 threads: 4 x 128 x 104 + 128 x 56 = 60 416 registers
@@ -83,7 +95,10 @@ using AtcCfg4 = AtcCfgT<4, 96, 16, 6, 104, 56, 32>;      // 640 threads: 4 x 128
 #ifndef ATC_X2_CW
 #define ATC_X2_CW 16
 #endif
-using AtcCfg6 = AtcCfgT<3, 64, 32, 6, 152, 56, 32, 1, 2>;   // 3 sets x 2 buffers x 64 keys, lean protocol; 512 threads
+// (3 sets x 2 alternating buffers x 64 keys, AtcCfgT<3, 64, 32, 6, 152, 56, 32, 1, 2>, was measured at 0.90 - 1.01 ms -- issue-bound, see
+// profiles/r02_attention_notes.md -- and is not instantiated: its fast build also showed an unresolved run-to-run race.)
+using AtcCfg3E = AtcCfgT<3, 128, 32, 5, 128, 40, 24, 1, 1, 56>;   // 3 x 128 + epilogue warpgroup; 640 threads: 384 x 128 + 128 x 40 + 128 x 56 = 61 440 registers
+using AtcCfg3EH = AtcCfgT<3, 128, 32, 5, 128, 40, 24, 1, 1, 56, true>;   // + PV starts on the first half of P
 using AtcCfg3L = AtcCfgT<3, 128, 32, 3, 152, 56, 24>;      // 3 x 128, lean protocol
 using AtcCfg3x2 = AtcCfgT<3, 128, ATC_X2_CW, 5, ATC_X2_REGS_SM, ATC_X2_REGS_AUX, 16, 2>;   // 896 threads: 6 x 128 x 80 + 128 x 24 = 64 512 registers
 
@@ -99,14 +114,6 @@ using AtcCfg3x2 = AtcCfgT<3, 128, ATC_X2_CW, 5, ATC_X2_REGS_SM, ATC_X2_REGS_AUX,
 #define ATC_T0() do { } while (0)
 #define ATC_ACC(var) do { } while (0)
 #endif
-
-typedef unsigned long long u64;
-__device__ __forceinline__ u64 f2_pack(uint32_t lo, uint32_t hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi)); return r; }
-__device__ __forceinline__ u64 f2_packf(float lo, float hi) { u64 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
-__device__ __forceinline__ void f2_unpack(u64 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
-__device__ __forceinline__ u64 f2_fma(u64 a, u64 b, u64 c) { u64 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
-__device__ __forceinline__ u64 f2_add(u64 a, u64 b) { u64 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
-__device__ __forceinline__ u64 f2_sub(u64 a, u64 b) { u64 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 
 // A chunk of W score columns of one TMEM lane in registers.  ld() is asynchronous: the values are defined after
 // tcgen05.wait::ld + fence() (the empty asm makes every later use depend on a point AFTER the wait; the loads are
@@ -145,6 +152,14 @@ template <> struct AtcChunk<16> {
 };
 __device__ __forceinline__ void tmem_st1(uint32_t taddr, uint32_t v) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(v) : "memory");
+}
+
+// k-steps [K0, K1) of P V (PHALF: the two halves of a tile are issued at different times)
+template <int K0, int K1, int KH>
+__device__ __forceinline__ void mma_pv_range(uint32_t tO, uint32_t tP, uint64_t vd, uint32_t idesc, uint32_t acc0) {
+#pragma unroll
+  for (int k = K0; k < K1; ++k)
+    mma_ts(tO, tP + uint32_t((k / KH) * (16 * KH) + 8 * (k % KH)), vd + uint64_t(128 * k), idesc, k == K0 ? acc0 : 1u);
 }
 
 // S[tS] = Q K^T: four K = 16 steps in ONE asm block (descriptor advance 32 B = +2 per step), so the issuing lane moves five
@@ -331,7 +346,8 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
   uint64_t* s_full = kv_empty + R;          // [NCH]  scores of the chain's current tile are in TMEM
   uint64_t* p_full = s_full + NCH;          // [NCH]  P written in place (4 warp arrivals)
   uint64_t* pv_done = p_full + NCH;         // [NCH]  PV of the chain's tile retired: its buffer may take the next scores
-  uint64_t* o_full = pv_done + NCH;         // [2]    last PV of the item retired
+  uint64_t* p_half = pv_done + NCH;         // [NCH]  (PHALF) P of the first half of the tile's keys written
+  uint64_t* o_full = p_half + NCH;          // [2]    last PV of the item retired
   uint64_t* o_empty = o_full + 2;           // [2]    epilogue has O, m_ref and the l partials of the item in registers (4 arrivals)
   uint64_t* mref_full = o_empty + 2;        // [2]    m_ref of the item published (4 arrivals)
   uint64_t* lpart_full = mref_full + 2;     // [2]    the row sums of all tiles of the item are in shared memory (one arrival: PV issuer)
@@ -367,7 +383,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       mbar_init(&lpart_full[i], 1);
     }
     for (int i = 0; i < R; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 2); }
-    for (int i = 0; i < NCH; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4 * NSPLIT); mbar_init(&pv_done[i], 1); }
+    for (int i = 0; i < NCH; ++i) { mbar_init(&s_full[i], 1); mbar_init(&p_full[i], 4 * NSPLIT); mbar_init(&pv_done[i], 1); mbar_init(&p_half[i], 4 * NSPLIT); }
     fence_mbar_init();
   }
   if (warp == SMW + 1) {
@@ -380,7 +396,105 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
   const uint32_t tmem_base = *tmem_slot;
   // TMEM columns: [0, NCH * BKV) score / P buffers, [384, 512) two O accumulators
 
-  if (warp >= SMW) {
+  const int half = (warp >> 2) % NSPLIT;                 // softmax / epilogue warps: which HW-column part of a tile the warp owns
+  const int row = (warp & 3) * 32 + lane;                // ... and their TMEM lane = query row of the tile
+  int n_bad = 0;
+  // coordinates of this CTA's item n, recomputed where they are needed (once per epilogue) instead of carried in registers
+  auto item_of = [&](const int n) {
+    const int it = int(blockIdx.x) + n * int(gridDim.x);
+    AtcItem x;
+    x.qt = it % nq;
+    const int r = it / nq;
+    x.h = r % p.H;
+    x.b = r / p.H;
+    return x;
+  };
+  // item n (coordinates `x`): O / l -> 16-bit, log-sum-exp.  Rows the fast path could not represent get a NaN sentinel in
+  // their first output word and are recomputed exactly after the main loop (keeps the function call and its register
+  // traffic out of the pipelined part of the kernel).
+  auto epilogue = [&](const int n) {
+    const AtcItem x = item_of(n);
+    const int par = n & 1;
+    const uint32_t ph = (n >> 1) & 1;
+    mbar_wait(&lpart_full[par], ph);
+    // the tiles' row sums are added in tile order, whichever chain produced them: the result does not depend on how this
+    // CTA's items happened to line up with the chains (a clip computed alone or inside a batch gives identical bits)
+    float l = 0.f;
+    for (int k = 0; k < nkv * NSPLIT; ++k) l += s_lpart[(par * Cfg::NKV_MAX * NSPLIT + k) * 128 + row];
+    float mr = s_mref[par * NSPLIT * 128 + row];
+    if (NSPLIT > 1) mr = fmaxf(mr, s_mref[(par * NSPLIT + 1) * 128 + row]);
+    mbar_wait(&o_full[par], ph);
+    tc_fence_after();
+    const uint32_t tO = tmem_base + 384u + uint32_t(par) * 64u + (uint32_t((warp & 3) * 32) << 16);
+    const int qrow = x.qt * ATT_BQ + row;
+    const float inv_l = 1.0f / l;
+    bool good = (l > 0.f) && (l < INFINITY);
+    typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.out) + size_t(x.b * p.N + qrow) * p.ld_out + x.h * ATT_D;
+    if (qrow < p.N && p.lse != nullptr) p.lse[(size_t(x.b) * p.H + x.h) * p.N + qrow] = mr + log2f(l);
+    // the 64 columns of O in parts of 32: both when the warp owns whole rows, part `half` when the columns are split
+#pragma unroll
+    for (int q = 0; q < 2 / NSPLIT; ++q) {
+      const int oh = half * (2 / NSPLIT) + q;
+      uint32_t v[32];
+      tmem_ld32(tO + uint32_t(oh * 32), v);
+      tc_wait_ld();
+      if (q == 2 / NSPLIT - 1) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&o_empty[par]);       // O, m_ref and the l partials of this slot are in registers
+      }
+      // one column suffices for the finiteness test: an inf / NaN in a row of P reaches all 64 columns of that row of O
+      // (the warp that owns column 0 decides, sets the sentinel and later redoes the WHOLE row)
+      if (oh == 0) {
+        good = good && (fabsf(__uint_as_float(v[0]) * inv_l) < INFINITY);
+#ifndef ATC_NOSOFTMAX
+        if (!good && qrow < p.N) ++n_bad;   // the first output word of the row becomes the NaN sentinel 0x7fff7fff
+#endif
+      }
+      if (qrow < p.N) {
+#pragma unroll
+        for (int i = 0; i < 32; i += 8)
+          st_global_v4(dst + oh * 32 + i,
+                       (oh == 0 && i == 0 && !good) ? 0x7fff7fffu : O16::pack(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
+                       O16::pack(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
+                       O16::pack(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
+                       O16::pack(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
+      }
+    }
+  };
+  // exact redo of the rows flagged by the epilogues this warp ran (none in the common case: one ballot).  Epilogue warpgroup: every
+  // item; chains: tile epi_j of item m + 1 belongs to chain ((m + 1) * nkv + 1) % NSET, and with split columns the warp that
+  // owns column 0 (the other half's warps may still be storing their part of a flagged row -- wait for all softmax warps).
+  auto redo_flagged_rows = [&](const int c) {
+    if (NSPLIT > 1) asm volatile("bar.sync 1, %0;" ::"n"(SMW * 32) : "memory");
+    if (__any_sync(0xffffffffu, n_bad != 0)) {
+      for (int m = 0; m < n_local; ++m) {
+        if (Cfg::EPIWG || (((m + 1) * nkv + 1) % NSET == c && half == 0)) {
+          const AtcItem x = item_of(m);
+          const int qrow = x.qt * ATT_BQ + row;
+          bool flagged = false;
+          if (qrow < p.N) {
+            const uint32_t w0 = *reinterpret_cast<const volatile uint32_t*>(reinterpret_cast<typename O16::T*>(p.out) + size_t(x.b * p.N + qrow) * p.ld_out + x.h * ATT_D);
+            flagged = (w0 == 0x7fff7fffu);
+          }
+          uint32_t bad = __ballot_sync(0xffffffffu, flagged);
+          while (bad) {
+            const int r = __ffs(bad) - 1;
+            bad &= bad - 1;
+            att_row_exact<DT>(p, qkv_base, x.b, x.h, x.qt * ATT_BQ + (warp & 3) * 32 + r, lane);
+          }
+        }
+      }
+    }
+  };
+
+  if (Cfg::EPIWG && warp >= SMW + 4) {
+    // ------------------------------------------------------------------ epilogue warpgroup: item after item, off the chains' path
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::EPIWG ? Cfg::REGS_EPI : 24));
+#pragma unroll 1
+    for (int n = 0; n < n_local; ++n) epilogue(n);
+    redo_flagged_rows(0);
+  } else if (warp >= SMW) {
   asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_AUX));
   if (warp == SMW) {
     // ------------------------------------------------------------------ TMA producer
@@ -534,8 +648,10 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       ATC_ACC(d_o);
       // the two per-tile barriers are tested together (a try_wait costs ~90 cycles even when the phase is long complete)
       const uint32_t ppar = (pbits >> c) & 1u;
-      const bool ok_p = mbar_try_wait(&p_full[c], ppar), ok_kv = mbar_try_wait(&kv_full[slot], phase);
-      if (!ok_p) mbar_wait(&p_full[c], ppar);
+      const bool early = Cfg::PHALF && j != nkv - 1;                    // full tile: start on the first half of P
+      uint64_t* pbar = early ? &p_half[c] : &p_full[c];
+      const bool ok_p = mbar_try_wait(pbar, ppar), ok_kv = mbar_try_wait(&kv_full[slot], phase);
+      if (!ok_p) mbar_wait(pbar, ppar);
       ATC_ACC(d_p);
       if (!ok_kv) mbar_wait(&kv_full[slot], phase);
       ATC_ACC(d_kv);
@@ -548,8 +664,16 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
       const uint32_t tO = tmem_base + 384u + uint32_t(n & 1) * 64u;
       const uint64_t vd = vdesc0 + uint64_t(slot * (SLOT_BYTES >> 4));
       const bool last = (j == nkv - 1);
+      if (early) {
+        if (elect_one()) mma_pv_range<0, BKV / 32, KH>(tO, tP, vd, idesc_pv, uint32_t(j));
+        __syncwarp();
+        mbar_wait(&p_full[c], ppar);
+        tc_fence_after();
+      }
       if (elect_one()) {
-        if (!last) {
+        if (early) {
+          mma_pv_range<BKV / 32, BKV / 16, KH>(tO, tP, vd, idesc_pv, 1u);
+        } else if (!last) {
           mma_pv<BKV / 16, KH>(tO, tP, vd, idesc_pv, uint32_t(j));
         } else {
           const int ksteps = nc_last >> 4;
@@ -664,8 +788,6 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(Cfg::REGS_SM));
     // ------------------------------------------------------------------ softmax chains: thread <-> query row (TMEM lane)
     const int c = warp / (4 * NSPLIT);
-    const int half = (warp >> 2) % NSPLIT;                 // which HW-column part of the chain's tiles this warp owns
-    const int row = (warp & 3) * 32 + lane;
     const uint32_t tS0 = tmem_base + uint32_t(half * HW) + (uint32_t((warp & 3) * 32) << 16);    // + buffer * BKV
     const float sc = p.scale_log2;
     const u64 sc2 = f2_packf(sc, sc);
@@ -674,70 +796,6 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
     const long long d_start = clock64();
     (void)d_start;
     float m_ref = 0.f;
-    int n_bad = 0;
-    // coordinates of this CTA's item n, recomputed where they are needed (once per epilogue) instead of carried in registers
-    auto item_of = [&](const int n) {
-      const int it = int(blockIdx.x) + n * int(gridDim.x);
-      AtcItem x;
-      x.qt = it % nq;
-      const int r = it / nq;
-      x.h = r % p.H;
-      x.b = r / p.H;
-      return x;
-    };
-    // item n (coordinates `x`): O / l -> 16-bit, log-sum-exp.  Rows the fast path could not represent get a NaN sentinel in
-    // their first output word and are recomputed exactly after the main loop (keeps the function call and its register
-    // traffic out of the pipelined part of the kernel).
-    auto epilogue = [&](const int n) {
-      const AtcItem x = item_of(n);
-      const int par = n & 1;
-      const uint32_t ph = (n >> 1) & 1;
-      mbar_wait(&lpart_full[par], ph);
-      // the tiles' row sums are added in tile order, whichever chain produced them: the result does not depend on how this
-      // CTA's items happened to line up with the chains (a clip computed alone or inside a batch gives identical bits)
-      float l = 0.f;
-      for (int k = 0; k < nkv * NSPLIT; ++k) l += s_lpart[(par * Cfg::NKV_MAX * NSPLIT + k) * 128 + row];
-      float mr = s_mref[par * NSPLIT * 128 + row];
-      if (NSPLIT > 1) mr = fmaxf(mr, s_mref[(par * NSPLIT + 1) * 128 + row]);
-      mbar_wait(&o_full[par], ph);
-      tc_fence_after();
-      const uint32_t tO = tmem_base + 384u + uint32_t(par) * 64u + (uint32_t((warp & 3) * 32) << 16);
-      const int qrow = x.qt * ATT_BQ + row;
-      const float inv_l = 1.0f / l;
-      bool good = (l > 0.f) && (l < INFINITY);
-      typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.out) + size_t(x.b * p.N + qrow) * p.ld_out + x.h * ATT_D;
-      if (qrow < p.N && p.lse != nullptr) p.lse[(size_t(x.b) * p.H + x.h) * p.N + qrow] = mr + log2f(l);
-      // the 64 columns of O in parts of 32: both when the warp owns whole rows, part `half` when the columns are split
-#pragma unroll
-      for (int q = 0; q < 2 / NSPLIT; ++q) {
-        const int oh = half * (2 / NSPLIT) + q;
-        uint32_t v[32];
-        tmem_ld32(tO + uint32_t(oh * 32), v);
-        tc_wait_ld();
-        if (q == 2 / NSPLIT - 1) {
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&o_empty[par]);       // O, m_ref and the l partials of this slot are in registers
-        }
-        // one column suffices for the finiteness test: an inf / NaN in a row of P reaches all 64 columns of that row of O
-        // (the warp that owns column 0 decides, sets the sentinel and later redoes the WHOLE row)
-        if (oh == 0) {
-          good = good && (fabsf(__uint_as_float(v[0]) * inv_l) < INFINITY);
-#ifndef ATC_NOSOFTMAX
-          if (!good && qrow < p.N) ++n_bad;   // the first output word of the row becomes the NaN sentinel 0x7fff7fff
-#endif
-        }
-        if (qrow < p.N) {
-#pragma unroll
-          for (int i = 0; i < 32; i += 8)
-            st_global_v4(dst + oh * 32 + i,
-                         (oh == 0 && i == 0 && !good) ? 0x7fff7fffu : O16::pack(__uint_as_float(v[i]) * inv_l, __uint_as_float(v[i + 1]) * inv_l),
-                         O16::pack(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
-                         O16::pack(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
-                         O16::pack(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
-        }
-      }
-    };
     // Masked keys (past the end of the clip, last KV tile only) get the score that maps to a = -120: p = 2^-120 is zero for
     // every purpose (0 in fp16, 7.5e-37 in bf16 against row sums >= 1) and stays inside the polynomial path's valid range.
     const float inv_sc = 1.0f / sc;
@@ -842,11 +900,19 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
 #ifdef ATC_NOSOFTMAX
         if (false)
 #endif
+        bool half_sent = false;
 #pragma unroll 1
         for (int col = 0; Cfg::PINGPONG && col < ncols; col += 2 * CW) {
           const bool has_b = col + CW < ncols, has_a2 = col + 2 * CW < ncols;
           if (has_b) cb.ld(tS + uint32_t(col + CW));
           att_chain_chunk<DT, ATT_CHAIN_NPOLY, CW>(ca.r, la, lb, amax, sc2, negm2);
+          if (Cfg::PHALF && col == 2 * CW) {     // P of keys 0 .. 2 CW - 1 was stored a whole chunk ago: its wait::st is free here
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&p_half[buf]);
+            half_sent = true;
+          }
           ca.st_lo(tS + uint32_t(col >> 1));
           if (has_b) {
             tc_wait_ld();
@@ -871,40 +937,19 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
         tc_wait_st();
         tc_fence_before();
         __syncwarp();
+        if (Cfg::PHALF && !half_sent && lane == 0) mbar_arrive(&p_half[buf]);   // short (last) tile: both at once
         if (lane == 0) mbar_arrive(&p_full[buf]);        // release: the row sums above and P in TMEM
         ATC_ACC(d_exp);
       }
       // deferred epilogue of the previous item: its last tile was g - 2, i.e. this (real or virtual) tile is tile 1 of item n
-      if (j == epi_j && n >= 1 && n <= n_local) epilogue(n - 1);  // (n > n_local: a virtual tile past the virtual item)
+      if (!Cfg::EPIWG && j == epi_j && n >= 1 && n <= n_local) epilogue(n - 1);  // (n > n_local: a virtual tile past the virtual item)
       ATC_ACC(d_epi);
       j += NSET;
       buf += NSET;
       if (buf >= NCH) buf -= NCH;
       while (j >= nkv) { j -= nkv; ++n; }
     }
-    // exact redo of the rows flagged above (none in the common case: one ballot).  Every warp re-walks the items whose epilogue
-    // it ran (tile 1 of item m + 1 belongs to chain ((m + 1) * nkv + 1) % NCH) and looks for the sentinel in its own rows.
-    // (split columns: the other half's warps may still be storing their part of a flagged row -- wait for all softmax warps)
-    if (NSPLIT > 1) asm volatile("bar.sync 1, %0;" ::"n"(SMW * 32) : "memory");
-    if (__any_sync(0xffffffffu, n_bad != 0)) {
-      for (int m = 0; m < n_local; ++m) {
-        if (((m + 1) * nkv + 1) % NSET == c && half == 0) {
-          const AtcItem x = item_of(m);
-          const int qrow = x.qt * ATT_BQ + row;
-          bool flagged = false;
-          if (qrow < p.N) {
-            const uint32_t w0 = *reinterpret_cast<const volatile uint32_t*>(reinterpret_cast<typename O16::T*>(p.out) + size_t(x.b * p.N + qrow) * p.ld_out + x.h * ATT_D);
-            flagged = (w0 == 0x7fff7fffu);
-          }
-          uint32_t bad = __ballot_sync(0xffffffffu, flagged);
-          while (bad) {
-            const int r = __ffs(bad) - 1;
-            bad &= bad - 1;
-            att_row_exact<DT>(p, qkv_base, x.b, x.h, x.qt * ATT_BQ + (warp & 3) * 32 + r, lane);
-          }
-        }
-      }
-    }
+    if (!Cfg::EPIWG) redo_flagged_rows(c);
 #ifdef ATC_DIAG
     if (p.lse != nullptr && lane == 0) {
       float* d = p.lse + size_t(blockIdx.x) * 512 + warp * 16;

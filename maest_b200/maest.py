@@ -205,7 +205,7 @@ class MAEST(nn.Module):
                  s_patchout_f_interleaved=0, s_patchout_t_indices=(), s_patchout_t_interleaved=0,
                  img_size=(96, 1875), patch_size=16, stride=(10, 10), in_chans=1, num_classes=400,
                  embed_dim=EMBED, depth=DEPTH, num_heads=HEADS, distilled=True, distilled_type="mean",
-                 op_dtype="fp16", attn_variant=3, fuse_ln=False):
+                 op_dtype="fp16", attn_variant=8, fuse_ln=False):
         super().__init__()
         if embed_dim != EMBED or num_heads != HEADS or patch_size != PATCH or in_chans != 1 or not distilled:
             raise NotImplementedError("the B200 path is specialised to ViT-Base/16, 12 heads, mono, distilled (all shipped MAEST configs)")

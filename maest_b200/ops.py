@@ -213,10 +213,12 @@ def ln_finalize(partials: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     return stats
 
 
-def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 3, save_lse: bool = False,
+def attention(qkv: torch.Tensor, B: int, N: int, heads: int = 12, variant: int = 8, save_lse: bool = False,
               out: Optional[torch.Tensor] = None):
     """qkv [B*N, 3*heads*64] 16-bit -> o [B*N, heads*64] 16-bit (and, for training, lse fp32 [B, heads, N]).
-    variant 3 (default): chains kernel, 3 x 128 keys (csrc/attention_chain.cuh); 4: 4 x 96 keys; 0 / 1 / 2: the round-1 kernels."""
+    variant 8 (default): chains kernel, 3 x 128 keys + epilogue warpgroup (csrc/attention_chain.cuh); 3: the same without the
+    epilogue warpgroup; 4: 4 x 96 keys; 5: split columns; 7: lean ring; 9: 8 + early PV;
+    0 / 1 / 2: the round-1 kernels (profiles/r02_attention_notes.md has the A/B of all of them)."""
     _need_cuda(qkv)
     assert qkv.is_contiguous() and qkv.shape == (B * N, 3 * heads * 64)
     if out is None:
@@ -382,7 +384,7 @@ def patch_tokens(mel: torch.Tensor, w_pe16: torch.Tensor, conv_bias, freq_pe, ti
 
 
 def encoder(x: torch.Tensor, B: int, N: int, block_table, n_blocks: int, last_attn_only: bool, op_dtype,
-            attn_variant: int = 3, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
+            attn_variant: int = 8, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Run n_blocks transformer blocks in place on the fp32 residual stream x [B*N, 768]."""
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()
