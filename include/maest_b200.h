@@ -248,9 +248,12 @@ int32_t maest_head_bwd_separated(const float* x, int32_t B, int32_t N, const flo
                                  float* d_head_ln_b, float* d_head_w, float* d_head_b, float* d_head_dist_w, float* d_head_dist_b,
                                  void* stream);
 
-/* LayerNorm backward (autograd of norm1 / norm2): dx += LN'(dy); dgamma/dbeta accumulated; optional op16 copy of the updated dx. */
+/* LayerNorm backward (autograd of norm1 / norm2): dx += LN'(dy); dgamma/dbeta accumulated; optional op16 copy of the updated dx;
+ * optional dx_colsum[768] += column sums of the UPDATED dx (the bias gradient of the linear layer that produced the normalised
+ * tensor's input: models/maest.py:418-419 -- saves a separate maest_colsum pass). */
 int32_t maest_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                            float* dx, void* dx16, int32_t op_dtype, float* dgamma, float* dbeta, int32_t rows, void* stream);
+                            float* dx, void* dx16, int32_t op_dtype, float* dgamma, float* dbeta, float* dx_colsum, int32_t rows,
+                            void* stream);
 
 /* out[n] += sum_m in[m,n]  (bias gradients); in: [M, N] of in_dtype with row stride ld. */
 int32_t maest_colsum(const void* in, int32_t in_dtype, int64_t ld, int32_t M, int32_t N, float* out, void* stream);

@@ -58,7 +58,7 @@ SIGNATURES = {
     "maest_bce_logits_fwd": (c_int32, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p, c_void_p]),
     "maest_head_bwd": (c_int32, [c_void_p, c_int32, c_int32] + [c_void_p] * 7 + [c_int32] + [c_void_p] * 9),
     "maest_head_bwd_separated": (c_int32, [c_void_p, c_int32, c_int32] + [c_void_p] * 9 + [c_int32] + [c_void_p] * 12),
-    "maest_layernorm_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_void_p, c_void_p, c_int32, c_void_p]),
+    "maest_layernorm_bwd": (c_int32, [c_void_p] * 7 + [c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_void_p]),
     "maest_colsum": (c_int32, [c_void_p, c_int32, c_int64, c_int32, c_int32, c_void_p, c_void_p]),
     "maest_cast_rows16": (c_int32, [c_void_p, c_void_p, c_int64, c_int32, c_int32, c_int32, c_int32, c_int32, c_void_p]),
     "maest_token_grad": (c_int32, [c_void_p] + [c_int32] * 7 + [c_void_p] * 7 + [c_void_p]),

@@ -382,7 +382,7 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   if (epilogue == MAEST_EPI_RESID32 && rows_per_group > 0) return fail(-1, "gemm: RESID32 does not support row remapping");
   if ((epilogue == MAEST_EPI_STORE16 || epilogue == MAEST_EPI_GELU16) && rows_per_group > 0) return fail(-1, "gemm: the 16-bit epilogues do not support row remapping");
   if (epilogue == MAEST_EPI_GELUBWD16 && !aux16) return fail(-1, "gemm: GELUBWD16 needs the saved pre-activation (aux16)");
-  if ((epilogue == MAEST_EPI_STORE16 || (epilogue == MAEST_EPI_GELU16 && !aux16)) &&
+  if ((epilogue == MAEST_EPI_STORE16 || (epilogue == MAEST_EPI_GELU16 && !aux16) || epilogue == MAEST_EPI_GELUBWD16) &&
       (r = make_tmap(&t_tmap_c, out, op_dtype, M, N, ld_out, 32))) return r;     // TMA-store epilogue: [32 rows x 64 columns] boxes
   cudaStream_t st = (cudaStream_t)stream;
   return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st)
@@ -771,14 +771,15 @@ int32_t maest_head_bwd_separated(const float* x, int32_t B, int32_t N, const flo
 }
 
 int32_t maest_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma,
-                            float* dx, void* dx16, int32_t op_dtype, float* dgamma, float* dbeta, int32_t rows, void* stream) {
+                            float* dx, void* dx16, int32_t op_dtype, float* dgamma, float* dbeta, float* dx_colsum, int32_t rows,
+                            void* stream) {
   if (rows <= 0) return 0;
   const int sms = g_num_sms[cur_device()] > 0 ? g_num_sms[cur_device()] : 148;
   int blocks = (rows + 7) / 8;
   if (blocks > sms * 4) blocks = sms * 4;
   cudaStream_t st = (cudaStream_t)stream;
-  if (op_dtype == MAEST_BF16) layernorm_bwd_kernel<DT_BF16><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, dx16, dgamma, dbeta, rows);
-  else if (op_dtype == MAEST_F16) layernorm_bwd_kernel<DT_F16><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, dx16, dgamma, dbeta, rows);
+  if (op_dtype == MAEST_BF16) layernorm_bwd_kernel<DT_BF16><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, dx16, dgamma, dbeta, dx_colsum, rows);
+  else if (op_dtype == MAEST_F16) layernorm_bwd_kernel<DT_F16><<<blocks, 256, 0, st>>>(dy, x, mean, rstd, gamma, dx, dx16, dgamma, dbeta, dx_colsum, rows);
   else return fail(-1, "layernorm_bwd: op_dtype must be f16/bf16");
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -129,6 +129,31 @@ __device__ __forceinline__ float gelu_erf_grad_fast(float x) {
   return fmaf(0.5f, erf_v, 0.5f) + x * e * 0.3989422804014327f;
 }
 
+// Two elements per call, packed fp32x2: Phi(-|x|) from the forward's polynomial (one MUFU), phi(x) from a second one;
+// 10.5 issue slots per element instead of ~20 with two MUFU each way (the fc2 input-gradient GEMM was epilogue-bound at 0.65 ms
+// against a 0.18 ms mainloop: 13 % of the training step).
+__device__ __forceinline__ void gelu_erf_grad_fast2(float x0, float x1, float& g0, float& g1) {
+  const u64 x = f2_packf(x0, x1);
+  const u64 ax = f2_packf(fminf(fabsf(x0), 5.65685425f), fminf(fabsf(x1), 5.65685425f));
+  u64 q = f2_fma(f2_packf(-5.775989393e-07f, -5.775989393e-07f), ax, f2_packf(3.963761264e-05f, 3.963761264e-05f));
+  q = f2_fma(q, ax, f2_packf(-7.848305395e-04f, -7.848305395e-04f));
+  q = f2_fma(q, ax, f2_packf(8.050128818e-03f, 8.050128818e-03f));
+  q = f2_fma(q, ax, f2_packf(-5.326407775e-02f, -5.326407775e-02f));
+  q = f2_fma(q, ax, f2_packf(-4.589391351e-01f, -4.589391351e-01f));
+  q = f2_fma(q, ax, f2_packf(-1.151135445e+00f, -1.151135445e+00f));
+  q = f2_fma(q, ax, f2_packf(-1.0f, -1.0f));                        // log2 Phi(-|x|)
+  const u64 z = f2_mul(f2_mul(x, x), f2_packf(-0.7213475204444817f, -0.7213475204444817f));   // -x^2 / 2 in log2 units
+  float q0, q1, z0, z1;
+  f2_unpack(q, q0, q1);
+  f2_unpack(z, z0, z1);
+  const float t0 = ex2_approx_ftz(q0), t1 = ex2_approx_ftz(q1);
+  const float e0 = ex2_approx_ftz(z0), e1 = ex2_approx_ftz(z1);
+  float u0, u1;
+  f2_unpack(f2_sub(f2_packf(1.0f, 1.0f), f2_packf(t0, t1)), u0, u1);
+  const u64 w = f2_mul(x, f2_packf(0.3989422804014327f, 0.3989422804014327f));
+  f2_unpack(f2_fma(w, f2_packf(e0, e1), f2_packf(x0 >= 0.f ? u0 : t0, x1 >= 0.f ? u1 : t1)), g0, g1);
+}
+
 // The staging tile is addressed in the shared window explicitly: through the generic pointer ptxas emitted generic LD.E / ST.E
 // (address-space resolution on every access) for what are plain ld.shared / st.shared.
 __device__ __forceinline__ void sts_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -212,8 +237,8 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
   // shared-memory traffic of staging fp32).  Measured with experiment builds (tools/gemm_diag.py): with no epilogue at all the
   // pair mainloops run at 1580-1600 TFLOP/s; reading the accumulator out of TMEM is free; for qkv the LSU global stores were
   // 0.048 of the 0.062 ms the epilogue added (hence the TMA store), for fc1 the GELU math is 0.09 ms and the stores 0.045 ms.
-  constexpr bool kPacked16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || kLnConsumer);
-  constexpr bool kTmaStore16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || kLnConsumer);   // single 16-bit output, no row remap
+  constexpr bool kPacked16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || kLnConsumer || EPI == EPI_GELUBWD16);
+  constexpr bool kTmaStore16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || kLnConsumer || EPI == EPI_GELUBWD16);   // single 16-bit output, no row remap
   float lane_r = 0.f, lane_mr = 0.f;   // LN consumer: rstd and -mean * rstd of row m0 + lane
   if constexpr (kLnConsumer) {
     if (m0 + lane < p.M) {
@@ -222,7 +247,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
       lane_mr = st.y;
     }
   }
-  load_resid(0);
+  if constexpr (EPI != EPI_GELUBWD16) load_resid(0);      // (GELUBWD16 fetches its pre-activation rows in the TMEM-load layout, below)
   const uint32_t stg_s = smem_u32(stg);
   // bias of the next chunk is fetched while the current one is processed (its L2 / L1 latency sat on the first FADD of every chunk)
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -242,12 +267,24 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
     // cc + 1 is in flight while chunk cc is processed), and the TMEM stage goes back to the MMA warp as soon as the last
     // chunk's load has completed.
     uint32_t va[32], vb[32];
+    // GELUBWD16: this thread's row of the saved pre-activation, 32 columns (64 contiguous bytes) per chunk, fetched one chunk
+    // ahead like the accumulator
+    uint4 ua[EPI == EPI_GELUBWD16 ? 4 : 1], ub[EPI == EPI_GELUBWD16 ? 4 : 1];
+    auto load_pre = [&](uint4 (&u)[EPI == EPI_GELUBWD16 ? 4 : 1], const int cc) {
+      if constexpr (EPI == EPI_GELUBWD16) {
+        const int n = n0 + cc * 32;
+        const bool ok = (m0 + lane < p.M) && (n + 32 <= p.N);
+        const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const typename O::T*>(p.aux16) + long(m0 + lane) * p.ld_out + n);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) u[q4] = ok ? src[q4] : make_uint4(0u, 0u, 0u, 0u);
+      }
+    };
     auto release_after_last_load = [&]() {
       tc_fence_before();
       __syncwarp();
       if (lane == 0) release_tmem();   // one arrival per warp: 8 (16 for a CTA pair, half of them remote) instead of 256 (512)
     };
-    auto process = [&](uint32_t (&v)[32], const int cc) {
+    auto process = [&](uint32_t (&v)[32], uint4 (&u)[EPI == EPI_GELUBWD16 ? 4 : 1], const int cc) {
       const int n = n0 + cc * 32;
 
       // lane = row: bias / fold vectors are warp-uniform (broadcast) loads; results are packed to 16 bits, written to a
@@ -270,6 +307,14 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
         if constexpr (EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || EPI == EPI_GELU16_LN) {
           gelu_erf_fast2(a.x, a.y, a.x, a.y);
           gelu_erf_fast2(a.z, a.w, a.z, a.w);
+        }
+        if constexpr (EPI == EPI_GELUBWD16) {     // d(pre-activation) = d(activation) * gelu'(pre-activation)
+          const uint32_t w0 = (j & 1) ? u[j >> 1].z : u[j >> 1].x, w1 = (j & 1) ? u[j >> 1].w : u[j >> 1].y;
+          const float2 u01 = O::unpack(w0), u23 = O::unpack(w1);
+          float g0, g1, g2, g3;
+          gelu_erf_grad_fast2(u01.x, u01.y, g0, g1);
+          gelu_erf_grad_fast2(u23.x, u23.y, g2, g3);
+          a.x *= g0; a.y *= g1; a.z *= g2; a.w *= g3;
         }
         o16[2 * j] = O::pack(a.x, a.y);
         o16[2 * j + 1] = O::pack(a.z, a.w);
@@ -324,22 +369,22 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
         }
       }
     };
-    if (nchunks > 0) tmem_ld32(taddr, va);
+    if (nchunks > 0) { tmem_ld32(taddr, va); load_pre(ua, 0); }
 #pragma unroll 1
     for (int cc = 0; cc < nchunks; cc += 2) {
       tc_wait_ld();
       reg_fence32(va);
       const bool has_b = cc + 1 < nchunks;
-      if (has_b) tmem_ld32(taddr + uint32_t((cc + 1) * 32), vb);
+      if (has_b) { tmem_ld32(taddr + uint32_t((cc + 1) * 32), vb); load_pre(ub, cc + 1); }
       else release_after_last_load();
-      process(va, cc);
+      process(va, ua, cc);
       if (has_b) {
         tc_wait_ld();
         reg_fence32(vb);
         const bool has_a = cc + 2 < nchunks;
-        if (has_a) tmem_ld32(taddr + uint32_t((cc + 2) * 32), va);
+        if (has_a) { tmem_ld32(taddr + uint32_t((cc + 2) * 32), va); load_pre(ua, cc + 2); }
         else release_after_last_load();
-        process(vb, cc + 1);
+        process(vb, ub, cc + 1);
       }
     }
     return;

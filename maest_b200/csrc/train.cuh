@@ -188,31 +188,38 @@ __global__ void __launch_bounds__(256) head_wgrad_kernel(const float* __restrict
 // ---------------------------------------------------------------------------------------------------------------
 // LayerNorm backward (autograd of norm1/norm2, models/maest.py:418-419): warp per row, strided over rows.
 //   dx[r] += rstd * (g - mean(g) - xhat * mean(g * xhat)),  g = dy * gamma;   dgamma += sum dy*xhat, dbeta += sum dy
-// Optionally also writes the updated dx as a 16-bit GEMM operand (dx16) for the next backward GEMMs.
+// Optionally also writes the updated dx as a 16-bit GEMM operand (dx16) for the next backward GEMMs, and accumulates the column
+// sums of the UPDATED dx into dx_colsum: that is the bias gradient of the linear layer whose output gradient this dx is (fc2 of
+// the previous block after norm1, proj of this block after norm2) -- it replaces a separate colsum pass over dx (331 MB read).
+// All three operands of a row (x, dy, dx) are requested before the first reduction, so a warp has 18 float4 loads in flight.
 // ---------------------------------------------------------------------------------------------------------------
 template <int DT>
 __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                             const float* __restrict__ mean, const float* __restrict__ rstd,
                                                             const float* __restrict__ gamma, float* __restrict__ dx,
                                                             void* __restrict__ dx16, float* __restrict__ dgamma,
-                                                            float* __restrict__ dbeta, int rows) {
+                                                            float* __restrict__ dbeta, float* __restrict__ dx_colsum, int rows) {
   using O = Op16<DT>;
   __shared__ float sred[8][D_MODEL];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int warps_total = gridDim.x * 8;
-  float4 gam[6], ag[6], ab[6];
+  float4 gam[6], ag[6], ab[6], ao[6];
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
     gam[i] = __ldg(reinterpret_cast<const float4*>(gamma) + lane + 32 * i);
     ag[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     ab[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    ao[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   for (int row = blockIdx.x * 8 + warp; row < rows; row += warps_total) {
     const float mu = mean[row], rs = rstd[row];
     const float4* xr = reinterpret_cast<const float4*>(x + long(row) * D_MODEL);
     const float4* dyr = reinterpret_cast<const float4*>(dy + long(row) * D_MODEL);
-    float4 xh[6], g[6];
+    float4* dxr = reinterpret_cast<float4*>(dx + long(row) * D_MODEL);
+    float4 xh[6], g[6], dxv[6];
     float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) dxv[i] = dxr[lane + 32 * i];
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
       const float4 xv = xr[lane + 32 * i], d = dyr[lane + 32 * i];
@@ -224,15 +231,15 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       s2 += (g[i].x * xh[i].x + g[i].y * xh[i].y) + (g[i].z * xh[i].z + g[i].w * xh[i].w);
     }
     const float m1 = warp_sum(s1) * (1.0f / D_MODEL), m2 = warp_sum(s2) * (1.0f / D_MODEL);
-    float4* dxr = reinterpret_cast<float4*>(dx + long(row) * D_MODEL);
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      float4 o = dxr[lane + 32 * i];
+      float4 o = dxv[i];
       o.x += rs * (g[i].x - m1 - xh[i].x * m2);
       o.y += rs * (g[i].y - m1 - xh[i].y * m2);
       o.z += rs * (g[i].z - m1 - xh[i].z * m2);
       o.w += rs * (g[i].w - m1 - xh[i].w * m2);
       dxr[lane + 32 * i] = o;
+      ao[i].x += o.x; ao[i].y += o.y; ao[i].z += o.z; ao[i].w += o.w;
       if (dx16 != nullptr) {
         uint2 pk;
         pk.x = O::pack(o.x, o.y);
@@ -242,11 +249,11 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
     }
   }
   // CTA-level reduction of dgamma / dbeta partials, then one atomic per column per CTA
-  for (int pass = 0; pass < 2; ++pass) {
+  for (int pass = 0; pass < (dx_colsum != nullptr ? 3 : 2); ++pass) {
     __syncthreads();
 #pragma unroll
     for (int i = 0; i < 6; ++i) {
-      const float4 v = pass == 0 ? ag[i] : ab[i];
+      const float4 v = pass == 0 ? ag[i] : pass == 1 ? ab[i] : ao[i];
       *reinterpret_cast<float4*>(&sred[warp][4 * (lane + 32 * i)]) = v;
     }
     __syncthreads();
@@ -254,7 +261,7 @@ __global__ void __launch_bounds__(256) layernorm_bwd_kernel(const float* __restr
       float t = 0.f;
 #pragma unroll
       for (int w = 0; w < 8; ++w) t += sred[w][c];
-      atomicAdd((pass == 0 ? dgamma : dbeta) + c, t);
+      atomicAdd((pass == 0 ? dgamma : pass == 1 ? dbeta : dx_colsum) + c, t);
     }
   }
 }

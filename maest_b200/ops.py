@@ -302,14 +302,16 @@ def bce_logits(logits: torch.Tensor, targets: torch.Tensor):
     return loss, dz
 
 
-def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, op_dtype, dx16: Optional[torch.Tensor] = None):
+def layernorm_bwd(dy, x, mean, rstd, gamma, dx, dgamma, dbeta, op_dtype, dx16: Optional[torch.Tensor] = None,
+                  dx_colsum: Optional[torch.Tensor] = None):
+    """dx += LN'(dy) (+ dgamma, dbeta); dx_colsum[768] += column sums of the updated dx (bias gradient of the layer upstream)."""
     _need_cuda(dy, x, dx)
     rows = x.numel() // 768
     with torch.cuda.device(x.device):
         lib = _lib_for(x)
         _lib.check(lib.maest_layernorm_bwd(dy.data_ptr(), x.data_ptr(), mean.data_ptr(), rstd.data_ptr(), gamma.data_ptr(),
                                            dx.data_ptr(), _p(dx16), op_dtype_code(op_dtype), dgamma.data_ptr(), dbeta.data_ptr(),
-                                           rows, _stream()), "layernorm_bwd")
+                                           _p(dx_colsum), rows, _stream()), "layernorm_bwd")
 
 
 def colsum(x: torch.Tensor, out: torch.Tensor):

@@ -171,23 +171,23 @@ class MaestTrainStep(torch.autograd.Function):
             x_in, mean1, rstd1, h1, qkv, lse, o, x_mid, mean2, rstd2, h2, upre, u = ctx.saved[i]
             # ---- MLP branch: x_out = x_mid + fc2(gelu(fc1(LN2(x_mid))))
             wgrad(dx16, u, E, 4 * E, pre + "mlp.fc2.weight")
-            ops.colsum(dx, G[pre + "mlp.fc2.bias"])
+            if i == len(model.blocks) - 1:     # every other fc2 / proj bias gradient comes out of the LayerNorm-backward kernel
+                ops.colsum(dx, G[pre + "mlp.fc2.bias"])   # that produced this dx (dx_colsum below)
             ops.gemm(dx16, w16(pre + "mlp.fc2"), _lib.EPI_GELUBWD16, M, 4 * E, E, b_mn=True, out=dupre, aux16=upre)
             wgrad(dupre, h2, 4 * E, E, pre + "mlp.fc1.weight")
             ops.colsum(dupre, G[pre + "mlp.fc1.bias"])
             ops.gemm(dupre, w16(pre + "mlp.fc1"), _lib.EPI_STORE32, M, E, 4 * E, b_mn=True, out=dh)
             ops.layernorm_bwd(dh, x_mid, mean2, rstd2, f32(pre + "norm2.weight"), dx, G[pre + "norm2.weight"], G[pre + "norm2.bias"],
-                              dt, dx16=dx16)
+                              dt, dx16=dx16, dx_colsum=G[pre + "attn.proj.bias"])
             # ---- attention branch: x_mid = x_in + proj(attn(qkv(LN1(x_in))))
             wgrad(dx16, o, E, E, pre + "attn.proj.weight")
-            ops.colsum(dx, G[pre + "attn.proj.bias"])
             ops.gemm(dx16, w16(pre + "attn.proj"), _lib.EPI_STORE16, M, E, E, b_mn=True, out=d_o)
             ops.attention_bwd(qkv, o, d_o, lse, B, N, 12, out=dqkv)
             wgrad(dqkv, h1, 3 * E, E, pre + "attn.qkv.weight")
             ops.colsum(dqkv, G[pre + "attn.qkv.bias"])
             ops.gemm(dqkv, w16(pre + "attn.qkv"), _lib.EPI_STORE32, M, E, 3 * E, b_mn=True, out=dh)
             ops.layernorm_bwd(dh, x_in, mean1, rstd1, f32(pre + "norm1.weight"), dx, G[pre + "norm1.weight"], G[pre + "norm1.bias"],
-                              dt, dx16=dx16)
+                              dt, dx16=dx16, dx_colsum=G[f"blocks.{i - 1}.mlp.fc2.bias"] if i > 0 else None)
             ctx.saved[i] = None
             reduce_range(blk_first[i], blk_end[i])
         # ---- token assembly + patch embedding

@@ -128,6 +128,10 @@ def test_layernorm_bwd_mixup_bce_units():
     dx, dg, db = dx0.clone().cuda(), torch.zeros(768).cuda(), torch.zeros(768).cuda()
     ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dx, dg, db, "fp16")
     assert rel(dx, dx0.double() + xd.grad) < 1e-5 and rel(dg, gd.grad) < 1e-5 and rel(db, bd.grad) < 1e-5
+    # fused bias gradient of the upstream linear layer: column sums of the UPDATED dx, accumulated onto what is already there
+    dx2, dg2, db2, cs = dx0.clone().cuda(), torch.zeros(768).cuda(), torch.zeros(768).cuda(), torch.ones(768).cuda()
+    ops.layernorm_bwd(dy.cuda(), x.cuda(), mean, rstd, gam.cuda(), dx2, dg2, db2, "fp16", dx_colsum=cs)
+    assert torch.equal(dx2, dx) and rel(cs, 1.0 + (dx0.double() + xd.grad).sum(0)) < 1e-5
     xm = torch.randn(4, 1, 96, 100, generator=g).half()
     perm, lam = torch.tensor([2, 0, 3, 1]), torch.tensor([0.9, 0.6, 0.75, 0.51])
     ref = xm.float() * lam.view(4, 1, 1, 1) + xm.float()[perm] * (1 - lam.view(4, 1, 1, 1))
