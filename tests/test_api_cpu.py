@@ -204,3 +204,11 @@ def test_checkpoint_argument_follows_the_reference(tmp_path):
     m3 = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, checkpoint=path, checkpoint_swa_weigts=False)
     assert not torch.equal(m3.state_dict()["blocks.3.attn.qkv.weight"], sd["blocks.3.attn.qkv.weight"])
     assert set(got) == set(base.state_dict())
+
+
+def test_graft_entry_build_runs():
+    """The driver's "does it build" check: __graft_entry__.build() compiles the library for sm_100a, loads it and checks the ABI
+    version against the binding's (a hard-coded number here once went stale when the ABI was bumped)."""
+    import importlib
+    g = importlib.import_module("__graft_entry__")
+    g.build()
