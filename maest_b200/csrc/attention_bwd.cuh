@@ -8,6 +8,11 @@
 // written as 16-bit tiles to shared memory in the SWIZZLE_128B layout, where the same bytes serve as a K-major
 // A operand (dQ) and as an MN-major A operand (dV, dK).  Q, K, dO are consumed in their natural [row][d] layout
 // (K-major for S / dP, MN-major B for dK / dQ / dV) — no transposes are materialised anywhere.
+// TWO compute warpgroups (round 2): warps w and w + 4 own the same 32 query rows (TMEM lanes) and split every row's 128 keys in
+// halves -- which are also the two [128 x 64] halves of the P / dS shared-memory tiles, the two 32-column halves of the dQ
+// staging tile and (at the end) dK vs dV.  With one warp per sub-partition the P / dS arithmetic (2 tcgen05.ld, one exponential,
+// ~12 instructions and two packs per score) was a 2500-cycle serial phase per (query tile, key tile) pair next to ~1800 cycles
+// of MMA issue; the kernel ran at 7300 cycles per pair.
 // dQ tiles are reduced across key tiles by the TMA engine (cp.reduce.async.bulk.tensor .add on fp32, staged through a
 // swizzled smem tile) into dq32; dK/dV are written once as 16-bit.
 #pragma once
@@ -15,7 +20,8 @@
 
 namespace mb {
 
-constexpr int ATTB_THREADS = 192;
+constexpr int ATTB_CWARPS = 8;                      // compute warps (two warpgroups)
+constexpr int ATTB_THREADS = (ATTB_CWARPS + 2) * 32; // + TMA warp + MMA warp
 constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 12 + 128;   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves), dQ staging (2 x [128 x 32] fp32)
 
 struct AttnBwdParams {
@@ -59,15 +65,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     printf("attention_bwd: dynamic smem base not 1024-aligned\n");
     __trap();
   }
-  if (warp == 5 && lane == 0) {
+  if (warp == ATTB_CWARPS + 1 && lane == 0) {
     mbar_init(kv_full, 1);
     for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
     mbar_init(sdp_full, 1);
-    mbar_init(pds_full, 128);
+    mbar_init(pds_full, ATTB_CWARPS * 32);
     mbar_init(mma2_done, 1);
     fence_mbar_init();
   }
-  if (warp == 4) {
+  if (warp == ATTB_CWARPS) {
     if (lane == 0) { tma_prefetch_desc(&tmap_qkv); tma_prefetch_desc(&tmap_do); tma_prefetch_desc(&tmap_dq); }
     tmem_alloc<512>(tmem_slot);
   }
@@ -77,7 +83,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
 
-  if (warp == 4) {
+  if (warp == ATTB_CWARPS) {
     if (lane == 0) {
       mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
       tma_load_2d(sK, &tmap_qkv, kv_full, p.H * 64 + h * 64, row_base + kv0);
@@ -92,7 +98,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
         if (++stage == 2) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == ATTB_CWARPS + 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(DT, 128, 128, 0, 0);    // S, dP: A K-major, B K-major
       constexpr uint32_t idesc_t = make_idesc(DT, 128, 64, 1, 1);     // dV, dK: A = P^T / dS^T (MN-major), B MN-major
@@ -144,18 +150,19 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       }
     }
   } else {
-    const int row = warp * 32 + lane;
-    const uint32_t lane_off = uint32_t(warp * 32) << 16;
+    const int wg = warp >> 2;                      // which half of the keys / staging columns / (dK | dV) this warp owns
+    const int row = (warp & 3) * 32 + lane;
+    const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const float sc = p.scale_log2, scale = p.scale;
     const long stat_base = (long(b) * p.H + h) * p.N;
-    auto compute_bar = [&]() { asm volatile("bar.sync 1, 128;" ::: "memory"); };
+    auto compute_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(ATTB_CWARPS * 32) : "memory"); };
     // dQ_i: TMEM -> swizzled smem -> global fp32 reduce-add by the TMA engine.  Rows of the tile that lie beyond this
     // clip carry dS = 0, hence dQ = 0, so adding them to the next clip's rows is harmless; rows beyond the tensor are clipped.
     auto drain_dq = [&](int i) {
       if (threadIdx.x == 0) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tile
       compute_bar();
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      {
+        const int c = wg;
         uint32_t v[32];
         tmem_ld32(tdQ + lane_off + uint32_t(c * 32), v);
         tc_wait_ld();
@@ -167,11 +174,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       fence_proxy_async_smem();
       tc_fence_before();
       compute_bar();
+#ifndef ATTB_DIAG_NO_REDUCE     // timing diagnostic: dQ is not accumulated (results wrong)
       if (threadIdx.x == 0) {
         tma_reduce_add_2d(&tmap_dq, sdQ, h * 64, row_base + i * 128);
         tma_reduce_add_2d(&tmap_dq, sdQ + ATT_TILE_BYTES, h * 64 + 32, row_base + i * 128);
         tma_store_commit();
       }
+#endif
     };
     for (int i = 0; i < nq; ++i) {
       const int qrow = i * 128 + row;
@@ -181,7 +190,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
+      for (int c = 2 * wg; c < 2 * wg + 2; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld32(tS + lane_off + uint32_t(c * 32), sv);
         tmem_ld32(tdP + lane_off + uint32_t(c * 32), dv);
@@ -199,7 +208,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           pkP[k >> 1] = O16::pack(p0, p1);
           pkD[k >> 1] = O16::pack(d0, d1);
         }
-        if (c == 0 && i > 0) {   // the previous iteration's GEMMs must retire before P/dS smem is overwritten
+        if (c == 2 * wg && i > 0) {   // the previous iteration's GEMMs must retire before P/dS smem is overwritten
           mbar_wait(mma2_done, (i - 1) & 1);
           tc_fence_after();
           drain_dq(i - 1);
@@ -220,12 +229,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     mbar_wait(mma2_done, (nq - 1) & 1);
     tc_fence_after();
     drain_dq(nq - 1);
-    if (threadIdx.x == 0) tma_store_wait<0>();
     // dK_j, dV_j -> 16-bit column blocks of dqkv
     const int key = kv0 + row;
     typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.dqkv16) + long(row_base + key) * (3 * p.H * 64) + h * 64;
-#pragma unroll 1
-    for (int which = 0; which < 2; ++which) {   // 0: dK -> column block 1, 1: dV -> column block 2
+    {
+      const int which = wg;                     // 0: dK -> column block 1, 1: dV -> column block 2
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         uint32_t v[32];
@@ -244,9 +252,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     }
   }
 
+  // the last reduce-add must have finished READING its staging tile before the CTA (and its shared memory) goes away; its global
+  // writes complete on their own before the grid does (waiting for them here cost ~2 us per CTA, after the dK / dV stores)
+  if (threadIdx.x == 0) tma_store_wait_read<0>();
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == ATTB_CWARPS) {
     tc_fence_after();
     tmem_dealloc<512>(tmem_base);
   }
