@@ -139,7 +139,9 @@ int32_t maest_layernorm_fwd(const float* x, const float* w, const float* b, void
 /* out = epilogue(A[M,K] W[N,K]^T): tcgen05 GEMM, A and W op16 (K contiguous, lda / ldw elements).  Replaces the nn.Linear /
  * Conv2d-as-GEMM calls listed at the MAEST_EPI_* enum.  Output row of GEMM row m:
  * (m / rows_per_group) * group_stride + row_offset + m % rows_per_group  (rows_per_group = 0 -> identity).
- * addend: optional fp32 [rows_per_group, N] table added in MAEST_EPI_STORE32.  N % 32 == 0, K % 8 == 0. */
+ * addend: optional fp32 [rows_per_group, N] table added in MAEST_EPI_STORE32; for MAEST_EPI_GELUBWD16 (maest_gemm) an optional fp32
+ * [N] vector the column sums of the OUTPUT are accumulated into (the fc1 bias gradient: saves a maest_colsum pass).
+ * N % 32 == 0, K % 8 == 0. */
 int32_t maest_linear_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, int32_t M,
                          int32_t N, int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out,
                          const float* resid, const float* addend, int32_t rows_per_group, int32_t group_stride,

@@ -49,6 +49,8 @@ struct GemmParams {
   void* out;             // 16-bit or fp32, row stride ld_out elements
   const float* resid;    // EPI_RESID32
   const float* addend;   // EPI_STORE32: optional [rows_per_group, N] table (pos-embed), else null
+                         // EPI_GELUBWD16: optional fp32 [N] the column sums of the output are ACCUMULATED into (written through
+                         // red.global: the bias gradient of the layer whose pre-activation gradient this GEMM produces)
   void* aux16;           // EPI_GELU16: optional second output, the pre-activation (saved for backward);
                          // EPI_GELUBWD16: input, the saved pre-activation.  Same shape / row stride as out.
   int ld_out;
@@ -291,6 +293,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
       // [32 rows x 64 B] tile (16-byte slots XOR-swizzled by (row >> 1) & 3: conflict-free both ways) and read back so that
       // 4 lanes cover one row's 64 contiguous bytes (a warp instruction stores 8 full row segments).
       uint32_t o16[16], pre16[16];
+      float cs[EPI == EPI_GELUBWD16 ? 32 : 1];     // GELUBWD16: this row's 32 output values (fp32) for the column sums below
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -315,9 +318,29 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
           gelu_erf_grad_fast2(u01.x, u01.y, g0, g1);
           gelu_erf_grad_fast2(u23.x, u23.y, g2, g3);
           a.x *= g0; a.y *= g1; a.z *= g2; a.w *= g3;
+          cs[4 * j] = a.x; cs[4 * j + 1] = a.y; cs[4 * j + 2] = a.z; cs[4 * j + 3] = a.w;
         }
         o16[2 * j] = O::pack(a.x, a.y);
         o16[2 * j + 1] = O::pack(a.z, a.w);
+      }
+      if constexpr (EPI == EPI_GELUBWD16) {
+        // bias gradient = column sums over the rows: thread = row here, so a transposing butterfly over the warp -- at distance
+        // 16, 8, .. 1 every lane keeps the half of its values whose column bit matches its lane bit and receives the partner's
+        // sums for that half: 31 shuffles + 31 adds, after which lane L holds the 32-row sum of column n + L.  Rows beyond M
+        // contribute exact zeros (their accumulator rows are zero).
+        if (p.addend != nullptr) {
+#pragma unroll
+          for (int w = 16; w >= 1; w >>= 1) {
+            const bool up = (lane & w) != 0;
+#pragma unroll
+            for (int k = 0; k < w; ++k) {
+              const float keep = up ? cs[k + w] : cs[k];
+              const float send = up ? cs[k] : cs[k + w];
+              cs[k] = keep + __shfl_xor_sync(0xffffffffu, send, w);
+            }
+          }
+          if (n + lane < p.N) atomicAdd(const_cast<float*>(p.addend) + n + lane, cs[0]);
+        }
       }
       if constexpr (kTmaStore16) {
         // The tile leaves through the TMA store engine: two 32-column chunks form a [32 rows x 128 B] SWIZZLE_128B tile in the

@@ -252,9 +252,11 @@ def attention_bwd(qkv: torch.Tensor, o: torch.Tensor, d_o: torch.Tensor, lse: to
 
 def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, M: int, N: int, K: int, a_mn: bool = False, b_mn: bool = False,
          bias: Optional[torch.Tensor] = None, out: Optional[torch.Tensor] = None, resid: Optional[torch.Tensor] = None,
-         aux16: Optional[torch.Tensor] = None, k_splits: int = 1) -> torch.Tensor:
-    """out[M,N] = epilogue(sum_k A(m,k) B(n,k)); a_mn / b_mn: operand stored [K, M] / [K, N] (see include/maest_b200.h)."""
-    _need_cuda(a, b, bias, out, resid, aux16)
+         aux16: Optional[torch.Tensor] = None, k_splits: int = 1, colsum_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out[M,N] = epilogue(sum_k A(m,k) B(n,k)); a_mn / b_mn: operand stored [K, M] / [K, N] (see include/maest_b200.h).
+    colsum_out (EPI_GELUBWD16 only): fp32 [N], the column sums of `out` are accumulated into it (the bias gradient)."""
+    _need_cuda(a, b, bias, out, resid, aux16, colsum_out)
+    assert colsum_out is None or (epilogue == _lib.EPI_GELUBWD16 and colsum_out.dtype == torch.float32 and colsum_out.numel() == N)
     assert a.dtype == b.dtype and a.dtype in (torch.float16, torch.bfloat16) and a.stride(-1) == 1 and b.stride(-1) == 1
     if out is None:
         odt = a.dtype if epilogue in (_lib.EPI_STORE16, _lib.EPI_GELU16, _lib.EPI_GELUBWD16) else torch.float32
@@ -264,7 +266,7 @@ def gemm(a: torch.Tensor, b: torch.Tensor, epilogue: int, M: int, N: int, K: int
     with torch.cuda.device(a.device):
         lib = _lib_for(a)
         _lib.check(lib.maest_gemm(a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn), _p(bias), M, N, K,
-                                  _TORCH2DT[a.dtype], epilogue, out.data_ptr(), out.stride(-2), _p(resid), None, 0, 0, 0,
+                                  _TORCH2DT[a.dtype], epilogue, out.data_ptr(), out.stride(-2), _p(resid), _p(colsum_out), 0, 0, 0,
                                   _p(aux16), int(k_splits), _stream()), "gemm")
     return out
 

@@ -173,9 +173,9 @@ class MaestTrainStep(torch.autograd.Function):
             wgrad(dx16, u, E, 4 * E, pre + "mlp.fc2.weight")
             if i == len(model.blocks) - 1:     # every other fc2 / proj bias gradient comes out of the LayerNorm-backward kernel
                 ops.colsum(dx, G[pre + "mlp.fc2.bias"])   # that produced this dx (dx_colsum below)
-            ops.gemm(dx16, w16(pre + "mlp.fc2"), _lib.EPI_GELUBWD16, M, 4 * E, E, b_mn=True, out=dupre, aux16=upre)
+            ops.gemm(dx16, w16(pre + "mlp.fc2"), _lib.EPI_GELUBWD16, M, 4 * E, E, b_mn=True, out=dupre, aux16=upre,
+                     colsum_out=G[pre + "mlp.fc1.bias"])       # fc1 bias gradient from the same epilogue (no colsum pass over dupre)
             wgrad(dupre, h2, 4 * E, E, pre + "mlp.fc1.weight")
-            ops.colsum(dupre, G[pre + "mlp.fc1.bias"])
             ops.gemm(dupre, w16(pre + "mlp.fc1"), _lib.EPI_STORE32, M, E, 4 * E, b_mn=True, out=dh)
             ops.layernorm_bwd(dh, x_mid, mean2, rstd2, f32(pre + "norm2.weight"), dx, G[pre + "norm2.weight"], G[pre + "norm2.bias"],
                               dt, dx16=dx16, dx_colsum=G[pre + "attn.proj.bias"])

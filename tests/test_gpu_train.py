@@ -91,6 +91,11 @@ def test_backward_gemm_variants(dt):
     up = upre.double().requires_grad_(True)
     torch.nn.functional.gelu(up).backward(dY.double() @ W.double())
     assert rel(ops.gemm(dY, W, _lib.EPI_GELUBWD16, Mt, Kin, Nout, b_mn=True, aux16=upre), up.grad) < tol16
+    # fused bias gradient: column sums of the (fp32) epilogue values accumulated onto what is already in the vector; Mt = 1732 is
+    # not a multiple of the 128-row tile, so the rows beyond M must contribute exact zeros
+    cs = torch.full((Kin,), 2.0, device="cuda")
+    out2 = ops.gemm(dY, W, _lib.EPI_GELUBWD16, Mt, Kin, Nout, b_mn=True, aux16=upre, colsum_out=cs)
+    assert rel(out2, up.grad) < tol16 and rel(cs - 2.0, up.grad.sum(0)) < 1e-4
     for splits in (1, 3, 7):
         dW = torch.zeros(Nout, Kin, device="cuda")
         ops.gemm(dY, X, _lib.EPI_ATOMIC32, Nout, Kin, Mt, a_mn=True, b_mn=True, out=dW, k_splits=splits)
