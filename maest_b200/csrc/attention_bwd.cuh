@@ -21,7 +21,7 @@
 namespace mb {
 
 constexpr int ATTB_CWARPS = 8;                      // compute warps (two warpgroups)
-constexpr int ATTB_THREADS = (ATTB_CWARPS + 2) * 32; // + TMA warp + MMA warp
+constexpr int ATTB_THREADS = (ATTB_CWARPS + 3) * 32; // + TMA warp + two MMA-issuing warps
 constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 12 + 128;   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves), dQ staging (2 x [128 x 32] fp32)
 
 struct AttnBwdParams {
@@ -67,10 +67,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   }
   if (warp == ATTB_CWARPS + 1 && lane == 0) {
     mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 2); }   // one commit per issuing warp
     mbar_init(sdp_full, 1);
     mbar_init(pds_full, ATTB_CWARPS * 32);
-    mbar_init(mma2_done, 1);
+    mbar_init(mma2_done, 2);
     fence_mbar_init();
   }
   if (warp == ATTB_CWARPS) {
@@ -130,11 +130,33 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           tc_fence_after();
           issue_s_dp(nstage);
         }
-        const uint32_t aQ = smem_u32(sQ + stage * ATT_TILE_BYTES), aO = smem_u32(sdO + stage * ATT_TILE_BYTES);
+        const uint32_t aO = smem_u32(sdO + stage * ATT_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // dV[key, d] += sum_q P[q, key] dO[q, d]
           mma_ss(tdV, make_sdesc(aP + uint32_t(k * 2048), 16384, 1024), make_sdesc(aO + uint32_t(k * 2048), 8192, 1024), idesc_t,
                  (i | k) ? 1u : 0u);
+        tc_commit(&qdo_empty[stage]);
+        tc_commit(mma2_done);
+        stage = nstage;
+        phase = nphase;
+      }
+    }
+  } else if (warp == ATTB_CWARPS + 2) {
+    // second issuing warp: dK and dQ (both read dS).  A single thread issues one tcgen05.mma per ~53 cycles whatever its N
+    // (profiles/r02_ubench_mma_issue.txt), so the 24 N = 64 instructions of an iteration were 1270 issue cycles on one warp;
+    // dV (other warp, own accumulator) and dK / dQ (this warp, own accumulators) need no order between them.
+    if (lane == 0) {
+      constexpr uint32_t idesc_t = make_idesc(DT, 128, 64, 1, 1);
+      constexpr uint32_t idesc_q = make_idesc(DT, 128, 64, 0, 1);
+      const uint32_t aK = smem_u32(sK), aDS = smem_u32(sdS);
+      mbar_wait(kv_full, 0);
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int i = 0; i < nq; ++i) {
+        mbar_wait(pds_full, i & 1);
+        mbar_wait(&qdo_full[stage], phase);
+        tc_fence_after();
+        const uint32_t aQ = smem_u32(sQ + stage * ATT_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // dK[key, d] += sum_q dS[q, key] Q[q, d]
           mma_ss(tdK, make_sdesc(aDS + uint32_t(k * 2048), 16384, 1024), make_sdesc(aQ + uint32_t(k * 2048), 8192, 1024), idesc_t,
@@ -145,8 +167,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
                  make_sdesc(aK + uint32_t(k * 2048), 8192, 1024), idesc_q, k ? 1u : 0u);
         tc_commit(&qdo_empty[stage]);
         tc_commit(mma2_done);
-        stage = nstage;
-        phase = nphase;
+        if (++stage == 2) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -187,6 +208,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       const bool q_ok = qrow < p.N;
       const float lse2 = q_ok ? p.lse[stat_base + qrow] : 0.f;
       const float dlt = q_ok ? p.delta[stat_base + qrow] : 0.f;
+      const bool full_tile = (kv0 + 128 <= p.N) && (i * 128 + 128 <= p.N);     // CTA-uniform
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
 #pragma unroll 1
@@ -196,17 +218,31 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
         tmem_ld32(tdP + lane_off + uint32_t(c * 32), dv);
         tc_wait_ld();
         uint32_t pkP[16], pkD[16];
+        // only the clip's last key tile and last query tile have rows / keys to mask: everywhere else the per-element
+        // compare + select pairs (30 % of this kernel's instructions, r02c_prof_attention_bwd) are skipped
+        if (full_tile) {
 #pragma unroll
-        for (int k = 0; k < 32; k += 2) {
-          const int key = kv0 + c * 32 + k;
-          float p0 = ex2_approx(fmaf(__uint_as_float(sv[k]), sc, -lse2));
-          float p1 = ex2_approx(fmaf(__uint_as_float(sv[k + 1]), sc, -lse2));
-          if (!q_ok || key >= p.N) p0 = 0.f;
-          if (!q_ok || key + 1 >= p.N) p1 = 0.f;
-          const float d0 = p0 * (__uint_as_float(dv[k]) - dlt) * scale;
-          const float d1 = p1 * (__uint_as_float(dv[k + 1]) - dlt) * scale;
-          pkP[k >> 1] = O16::pack(p0, p1);
-          pkD[k >> 1] = O16::pack(d0, d1);
+          for (int k = 0; k < 32; k += 2) {
+            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[k]), sc, -lse2));
+            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[k + 1]), sc, -lse2));
+            const float d0 = p0 * (__uint_as_float(dv[k]) - dlt) * scale;
+            const float d1 = p1 * (__uint_as_float(dv[k + 1]) - dlt) * scale;
+            pkP[k >> 1] = O16::pack(p0, p1);
+            pkD[k >> 1] = O16::pack(d0, d1);
+          }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 32; k += 2) {
+            const int key = kv0 + c * 32 + k;
+            float p0 = ex2_approx(fmaf(__uint_as_float(sv[k]), sc, -lse2));
+            float p1 = ex2_approx(fmaf(__uint_as_float(sv[k + 1]), sc, -lse2));
+            if (!q_ok || key >= p.N) p0 = 0.f;
+            if (!q_ok || key + 1 >= p.N) p1 = 0.f;
+            const float d0 = p0 * (__uint_as_float(dv[k]) - dlt) * scale;
+            const float d1 = p1 * (__uint_as_float(dv[k + 1]) - dlt) * scale;
+            pkP[k >> 1] = O16::pack(p0, p1);
+            pkD[k >> 1] = O16::pack(d0, d1);
+          }
         }
         if (c == 2 * wg && i > 0) {   // the previous iteration's GEMMs must retire before P/dS smem is overwritten
           mbar_wait(mma2_done, (i - 1) & 1);

@@ -10,7 +10,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-ROLE = {"gemm2_tn_kernel<0, 0>": "gemm_qkv", "gemm_tn_kernel<0, 2, 0, 0>": "gemm_proj", "gemm_tn_kernel<0, 1, 0, 0>": "gemm_fc1",
+ROLE = {"gemm2_tn_kernel<0, 0>": "gemm_qkv", "gemm2_tn_kernel<0, 1>": "gemm_fc1", "gemm_tn_kernel<0, 2, 0, 0>": "gemm_proj", "gemm_tn_kernel<0, 1, 0, 0>": "gemm_fc1",
         "gemm2_tn_kernel<0, 2>": "gemm_fc2", "gemm_tn_kernel<0, 0, 0, 0>": "gemm_qkv"}
 
 

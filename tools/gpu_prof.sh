@@ -14,7 +14,7 @@ ncu --set full --clock-control none --import-source on -k regex:mel_ingest -s 4 
     python bench.py --mode ingest --steps 3 > gpurun_out/ncu_mel_ingest.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:attention_bwd -s 2 -c 1 -o gpurun_out/prof_attention_bwd -f \
     python bench.py --mode train --batch 16 --steps 1 --warmup 3 > gpurun_out/ncu_attention_bwd.log 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -s 1116 -c 372 --csv --log-file gpurun_out/launches_train.csv \
+ncu --metrics gpu__time_duration.sum --clock-control none -s 1020 -c 340 --csv --log-file gpurun_out/launches_train.csv \
     python bench.py --mode train --steps 1 --warmup 3 > gpurun_out/ncu_train.log 2>&1
 # the .ncu-rep files are too large to travel back (64 MiB cap): summarise them here, keep only the text
 export NCU_SUMMARY_DIR=gpurun_out/profiles_out
