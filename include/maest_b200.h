@@ -131,6 +131,20 @@ int32_t maest_patch_tokens_fwd(const void* mel, int32_t mel_dtype, int32_t B, in
                                const float* new_pos_embed, const int32_t* keep_ft, int32_t P, int32_t t_offset,
                                float* tokens, void* workspace, size_t workspace_bytes, void* stream);
 
+/* K1 + K2 in one call: waveform in, packed token buffer out (SURVEY.md section 8(b) `maest_wave_tokens_fwd`).  Replaces
+ * MelSpectrogram.forward + PatchEmbed.forward + the pre-block part of forward_features for the waveform path of
+ * MAEST.forward (models/maest.py:862-903 -> :634-800).  Two kernel sequences on `stream` (log-mel, then gather / pos table /
+ * patch GEMM); the fp32 mel [B, 96, T] lives in the first 4*B*96*T bytes (rounded up to 256) of `workspace`, followed by the
+ * K2 workspace -- it never goes back to the caller.  T = 1 + S/256 (the batched waveform path, which the reference does not
+ * trim, :890-892; the 1-D chunking path that trims 626 -> 625 frames keeps the two separate calls).
+ * workspace_bytes >= maest_wave_tokens_workspace_bytes(B, S, P). */
+size_t maest_wave_tokens_workspace_bytes(int32_t B, int32_t S, int32_t P);
+int32_t maest_wave_tokens_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, const void* w_pe,
+                              int32_t op_dtype, const float* conv_bias, const float* freq_pe, int32_t Fp, const float* time_pe,
+                              int32_t Wt, const float* cls_token, const float* dist_token, const float* new_pos_embed,
+                              const int32_t* keep_ft, int32_t P, int32_t t_offset, float* tokens, void* workspace,
+                              size_t workspace_bytes, void* stream);
+
 /* LayerNorm over 768-wide rows, fp32 in -> op16 out (GEMM operand).  Replaces norm1/norm2, models/maest.py:395,405,418-419.
  * mean/rstd (fp32 [rows]) are optional saves for the backward pass (may be NULL). */
 int32_t maest_layernorm_fwd(const float* x, const float* w, const float* b, void* y16, int32_t op_dtype, int32_t rows,

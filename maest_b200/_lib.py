@@ -40,6 +40,10 @@ SIGNATURES = {
     "maest_patch_tokens_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_int32, c_void_p, c_void_p,
                                          c_int32, c_void_p, c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32,
                                          c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "maest_wave_tokens_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int32]),
+    "maest_wave_tokens_fwd": (c_int32, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p,
+                                        c_int32, c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_size_t,
+                                        c_void_p]),
     "maest_layernorm_fwd": (c_int32, [c_void_p, c_void_p, c_void_p, c_void_p, c_int32, c_int32, c_float, c_void_p,
                                       c_void_p, c_void_p]),
     "maest_linear_fwd": (c_int32, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int32, c_int32, c_int32, c_int32,

@@ -575,6 +575,28 @@ int32_t maest_patch_tokens_fwd(const void* mel, int32_t mel_dtype, int32_t B, in
                           pos, P, 2 + P, 2, stream);
 }
 
+size_t maest_wave_tokens_workspace_bytes(int32_t B, int32_t S, int32_t P) {
+  const size_t mel = (size_t(B) * LM_NMEL * size_t(1 + S / LM_HOP) * 4 + 255) & ~size_t(255);
+  return mel + maest_patch_workspace_bytes(B, P);
+}
+
+int32_t maest_wave_tokens_fwd(const float* wav, int32_t B, int32_t S, int64_t wav_stride, const void* w_pe, int32_t op_dtype,
+                              const float* conv_bias, const float* freq_pe, int32_t Fp, const float* time_pe, int32_t Wt,
+                              const float* cls_token, const float* dist_token, const float* new_pos_embed, const int32_t* keep_ft,
+                              int32_t P, int32_t t_offset, float* tokens, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0) return 0;
+  if (workspace_bytes < maest_wave_tokens_workspace_bytes(B, S, P)) return fail(-1, "wave_tokens: workspace too small");
+  if (reinterpret_cast<uintptr_t>(workspace) & 255) return fail(-4, "wave_tokens: workspace must be 256-byte aligned");
+  const int T = 1 + S / LM_HOP;
+  const size_t mel_bytes = (size_t(B) * LM_NMEL * size_t(T) * 4 + 255) & ~size_t(255);
+  float* mel = reinterpret_cast<float*>(workspace);
+  int r;
+  if ((r = logmel_launch(wav, B, S, wav_stride, mel, nullptr, stream))) return r;
+  return maest_patch_tokens_fwd(mel, MAEST_F32, B, T, w_pe, op_dtype, conv_bias, freq_pe, Fp, time_pe, Wt, cls_token, dist_token,
+                                new_pos_embed, keep_ft, P, t_offset, tokens, reinterpret_cast<uint8_t*>(workspace) + mel_bytes,
+                                workspace_bytes - mel_bytes, stream);
+}
+
 size_t maest_encoder_workspace_bytes(int64_t rows) {
   // h16 [rows,768] | qkv16 [rows,2304] | o16 [rows,768] | u16 [rows,3072]  (+ 128 rows of slack per buffer) | LN stats [rows,2] fp32
   // | LN stats [rows,2] fp32 | LN partials [24,rows,4] fp32

@@ -387,6 +387,28 @@ def patch_tokens(mel: torch.Tensor, w_pe16: torch.Tensor, conv_bias, freq_pe, ti
     return tokens
 
 
+def wave_tokens(wav: torch.Tensor, w_pe16: torch.Tensor, conv_bias, freq_pe, time_pe, cls_token, dist_token, new_pos_embed,
+                keep_ft: Optional[torch.Tensor] = None, t_offset: int = 0) -> torch.Tensor:
+    """K1 + K2 in ONE C-ABI call: waveform [B, S] fp32 -> tokens fp32 [B, 2+P, 768] (the mel stays in the call's workspace)."""
+    _need_cuda(wav, w_pe16)
+    assert wav.dim() == 2 and wav.dtype == torch.float32 and wav.stride(-1) == 1
+    B, S = wav.shape
+    T = 1 + S // 256
+    Fp, Tp = 9, (T - 16) // 10 + 1
+    Wt = time_pe.shape[-1]
+    P = Fp * Tp if keep_ft is None else int(keep_ft.numel())
+    tokens = torch.empty((B, 2 + P, 768), device=wav.device, dtype=torch.float32)
+    with torch.cuda.device(wav.device):
+        lib = _lib_for(wav)
+        ws_bytes = lib.maest_wave_tokens_workspace_bytes(B, S, P)
+        ws = torch.empty(ws_bytes, device=wav.device, dtype=torch.uint8)
+        _lib.check(lib.maest_wave_tokens_fwd(
+            wav.data_ptr(), B, S, wav.stride(0), w_pe16.data_ptr(), _TORCH2DT[w_pe16.dtype], conv_bias.data_ptr(), freq_pe.data_ptr(),
+            Fp, time_pe.data_ptr(), Wt, cls_token.data_ptr(), dist_token.data_ptr(), new_pos_embed.data_ptr(), _p(keep_ft), P,
+            int(t_offset), tokens.data_ptr(), ws.data_ptr(), ws_bytes, _stream()), "wave_tokens")
+    return tokens
+
+
 def encoder(x: torch.Tensor, B: int, N: int, block_table, n_blocks: int, last_attn_only: bool, op_dtype,
             attn_variant: int = 8, workspace: Optional[torch.Tensor] = None) -> torch.Tensor:
     """Run n_blocks transformer blocks in place on the fp32 residual stream x [B*N, 768]."""

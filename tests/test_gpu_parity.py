@@ -466,3 +466,24 @@ def test_tensor_map_cache_serves_repeat_calls():
         lib.maest_tmap_cache_stats(ctypes.byref(h), ctypes.byref(m))
     assert torch.equal(a, b) and torch.equal(b, c)
     assert h.value - h0 >= 100 and m.value - m0 <= 8, (h.value - h0, m.value - m0)
+
+
+@pytest.mark.gpu
+def test_wave_tokens_one_call_equals_k1_then_k2():
+    """maest_wave_tokens_fwd (K1 + K2 behind one C-ABI entry) gives the bits of maest_logmel_fwd followed by
+    maest_patch_tokens_fwd, with and without patchout."""
+    model = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False, s_patchout_t=20, s_patchout_f=2)
+    model.load_state_dict(synth.synth_state_dict(62, 400, seed=0), strict=False)
+    model = model.cuda()
+    x = synth.wave_a(3, 160000).cuda()
+    args = (model._weight16("patch_embed.proj", model.patch_embed.proj.weight), model._f32(model.patch_embed.proj.bias),
+            model._f32(model.freq_new_pos_embed).reshape(768, -1), model._f32(model.time_new_pos_embed).reshape(768, -1),
+            model._f32(model.cls_token).reshape(-1), model._f32(model.dist_token).reshape(-1), model._f32(model.new_pos_embed).reshape(2, 768))
+    mel = ops.logmel(x)
+    assert torch.equal(ops.wave_tokens(x, *args), ops.patch_tokens(mel, *args))
+    keep = ops.keep_ft_tensor(torch.tensor([0, 2, 3, 5, 6, 7, 8]), torch.arange(0, 62, 2), 9, 62, None, x.device)
+    a = ops.wave_tokens(x, *args, keep_ft=keep)
+    b = ops.patch_tokens(mel, *args, keep_ft=keep)
+    with pytest.raises(Exception, match="larger than the expected time encodings"):      # models/maest.py:664-668
+        ops.wave_tokens(x, *args, t_offset=3)
+    assert a.shape == (3, 2 + 7 * 31, 768) and torch.equal(a, b)
