@@ -280,7 +280,7 @@ class MAEST(nn.Module):
         new = cls.__new__(cls)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
-            if k in ("_w16", "_ws", "_block_table"):
+            if k in ("_w16", "_ws", "_block_table", "_graphs", "_graph_version"):
                 continue
             setattr(new, k, copy.deepcopy(v, memo))
         new._w16, new._ws, new._block_table = {}, None, None
@@ -466,6 +466,46 @@ class MAEST(nn.Module):
         dev = self._device()
         if dev.type != "cuda":
             raise RuntimeError("maest_b200: move the model to a CUDA device (B200, sm_100a); there is no CPU path")
+        if getattr(self, "use_cuda_graphs", False) and not self.training and x.dim() in (1, 2) and not torch.is_grad_enabled():
+            return self._forward_graphed(x, transformer_block, return_self_attention, melspectrogram_input)
+        return self._forward_eager(x, transformer_block, return_self_attention, melspectrogram_input)
+
+    def _forward_graphed(self, x, transformer_block, return_self_attention, melspectrogram_input):
+        """Opt-in (`model.use_cuda_graphs = True`, eval mode, waveform / 2-D mel inputs): the ~90 dependent launches of one forward
+        are captured ONCE per (input shape, options, weight version) into a CUDA graph and replayed -- small-batch calls
+        (predict_labels on one file) are bound by launch gaps, not by the kernels.  Every buffer the captured kernels touch (static
+        input, encoder workspace, 16-bit weight copies, outputs) is kept alive by the cache entry; outputs are cloned."""
+        dev = self._device()
+        version = (sum(int(p._version) for p in self.parameters()), self.cls_token.data_ptr(), self.head[1].weight.data_ptr())
+        if getattr(self, "_graph_version", None) != version:
+            self._graphs, self._graph_version = {}, version
+        key = (tuple(x.shape), x.dtype, int(transformer_block), bool(return_self_attention), bool(melspectrogram_input),
+               self.op_dtype, self.attn_variant, self.fuse_ln, self.distilled_type)
+        ent = self._graphs.get(key)
+        if ent is None:
+            if len(self._graphs) >= 8:
+                self._graphs.pop(next(iter(self._graphs)))
+            static_in = torch.empty(x.shape, dtype=x.dtype, device=dev)
+            static_in.copy_(x)
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                for _ in range(2):      # stages the 16-bit weight copies and the workspace outside the capture
+                    self._forward_eager(static_in, transformer_block, return_self_attention, melspectrogram_input)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                out = self._forward_eager(static_in, transformer_block, return_self_attention, melspectrogram_input)
+            ent = (graph, static_in, out, self._ws, list(self._w16.values()) if hasattr(self, "_w16") else None)
+            self._graphs[key] = ent
+        graph, static_in, out = ent[0], ent[1], ent[2]
+        static_in.copy_(x, non_blocking=True)
+        graph.replay()
+        return tuple(None if o is None else o.clone() for o in out)
+
+    def _forward_eager(self, x, transformer_block: int = -1, return_self_attention: bool = False,
+                       melspectrogram_input: bool = False):
+        dev = self._device()
         caller_x = x
         if x.device != dev:
             x = x.to(dev, non_blocking=True)

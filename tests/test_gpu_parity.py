@@ -487,3 +487,30 @@ def test_wave_tokens_one_call_equals_k1_then_k2():
     with pytest.raises(Exception, match="larger than the expected time encodings"):      # models/maest.py:664-668
         ops.wave_tokens(x, *args, t_offset=3)
     assert a.shape == (3, 2 + 7 * 31, 768) and torch.equal(a, b)
+
+
+@pytest.mark.gpu
+def test_cuda_graph_forward_is_identical_and_tracks_weight_updates():
+    """model.use_cuda_graphs (opt-in): replayed forwards return the eager bits for waveform and mel inputs and for a block
+    embedding; an in-place weight update (new parameter version) drops the captured graphs."""
+    model = get_maest(arch="discogs-maest-10s-pw-129e", pretrained=False)
+    model.load_state_dict(synth.synth_state_dict(62, 400, seed=0), strict=False)
+    model = model.cuda().eval()
+    x2 = synth.wave_a(2, 160000).cuda()
+    x1 = synth.wave_a(1, 21 * 16000)[0].cuda()              # 1-D, 21 s -> 2 chunks
+    with torch.no_grad():
+        ref2, ref1, ref6 = model(x2), model(x1), model(x2, transformer_block=6)
+        model.use_cuda_graphs = True
+        for _ in range(3):                                   # capture, then replays
+            got2, got1, got6 = model(x2), model(x1), model(x2, transformer_block=6)
+            assert torch.equal(got2[0], ref2[0]) and torch.equal(got2[1], ref2[1])
+            assert torch.equal(got1[0], ref1[0]) and got6[0] is None and torch.equal(got6[1], ref6[1])
+        y = model(x2 * 0.5)                                  # same shape, new data: replay reads the refreshed static input
+        model.use_cuda_graphs = False
+        assert torch.equal(y[0], model(x2 * 0.5)[0])
+        model.use_cuda_graphs = True
+        model.head[1].bias.add_(1.0)                         # version bump -> graphs dropped, new capture sees the new weights
+        z = model(x2)
+        assert float((z[0] - (ref2[0] + 1.0)).abs().max()) < 1e-5
+    import copy
+    assert copy.deepcopy(model) is not None                  # the graph cache is not copied (SWA deep-copies the net)

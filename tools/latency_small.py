@@ -6,11 +6,12 @@ sys.path.insert(0, ROOT)
 import torch
 from maest_b200 import get_maest, synth
 
-out = {"tmap_cache": os.environ.get("MAEST_TMAP_CACHE", "1")}
+out = {"tmap_cache": os.environ.get("MAEST_TMAP_CACHE", "1"), "cuda_graphs": os.environ.get("MAEST_CUDA_GRAPHS", "0")}
 for arch, S, grid_t in (("discogs-maest-10s-fs-129e", 160000, 62), ("discogs-maest-30s-pw-129e", 480000, 187)):
     model = get_maest(arch=arch, pretrained=False)
     model.load_state_dict(synth.synth_state_dict(grid_t, 400, seed=0), strict=False)
     model = model.cuda().eval()
+    model.use_cuda_graphs = os.environ.get("MAEST_CUDA_GRAPHS") == "1"
     for B in (1, 4):
         x = synth.wave_a(B, S).cuda()
         with torch.no_grad():
