@@ -281,7 +281,9 @@ def train_leg(args, steps: int, warmup: int, B: int):
     net = get_maest(arch="passt_s_swa_p16_128_ap476", pretrained=False, n_classes=400, input_f=96, input_t=1875, s_patchout_t=90, op_dtype=op)
     net.load_state_dict(synth.synth_state_dict(187, 400, seed=0), strict=False)
     if world > 1:
-        net.grad_allreduce = True          # ONE flat fp32 NCCL all-reduce of the gradient buffer after the last backward kernel
+        # ONE flat NCCL all-reduce of the gradient buffer after the last backward kernel: fp32 (the reference's DDP semantics) unless
+        # MAEST_ALLREDUCE=bf16 asks for the compressed variant
+        net.grad_allreduce = "bf16" if os.environ.get("MAEST_ALLREDUCE") == "bf16" else True
     net.allreduce_events = []              # (start, end) CUDA events around that all-reduce, one pair per step (train.py)
     mod = Module(net=net, mixup_alpha=0.3, do_swa=False).to(dev).train()
     from maest_b200.optim import FusedAdamW
@@ -345,9 +347,10 @@ def train_leg(args, steps: int, warmup: int, B: int):
                     config=dict(workload=f"maest_30s_from_passt_pretrain training step: mel [{B},1,96,1875] fp16 per GPU, s_patchout_t=90 -> {N} tokens, "
                                          "mixup 0.3, BCE, fwd+bwd" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + AdamW step",
                                 batch_per_gpu=B, tokens=N, gflop_per_clip_fwd=fl["total"] / 1e9),
-                    loss=float(loss.detach()), grad_elements_allreduced=n_grad[0], allreduce_bytes=4 * n_grad[0],
-                    allreduce_ms_exposed=ar_ms, allreduce="one flat fp32 dist.all_reduce (NCCL) after the last backward kernel, not overlapped"
-                    if world > 1 else "none (1 GPU)", clocks=clocks,
+                    loss=float(loss.detach()), grad_elements_allreduced=n_grad[0], allreduce_bytes=(2 if net.grad_allreduce == "bf16" else 4) * n_grad[0],
+                    allreduce_ms_exposed=ar_ms, allreduce=("one flat " + ("bf16-compressed" if net.grad_allreduce == "bf16" else "fp32") +
+                               " dist.all_reduce (NCCL) after the last backward kernel, not overlapped") if world > 1 else "none (1 GPU)",
+                    clocks=clocks,
                     model_tflops=tf, model_frac_of_bf16_sustained=tf / peaks["bf16_tflops_sustained"],
                     gpu_launches=steps * (12 * 30 + 12))
     del mod, net, opt
