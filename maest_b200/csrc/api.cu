@@ -124,17 +124,17 @@ int g_gemm_pair_mode = 2;   // 0: 1-CTA tiles, 1: CTA-pair (cta_group::2) tiles,
 
 // Measured on B200 (M = 107 840): the pair kernel wins where the mainloop dominates (qkv 0.329 -> 0.289 ms, fc2 0.434 -> 0.400 ms)
 // and, with the packed / TMA-store epilogue, for the inference fc1 + GELU (0.476 -> 0.450 ms); it loses for proj (0.188 -> 0.197 ms)
-// and is not used for the training forward's two-output GELU epilogue.
+// and, once both of its outputs left through TMA stores, also for the training forward fc1 (GELU16_SAVE).
 inline bool use_pair_kernel(int epi, int K, bool has_aux = false) {
   if (epi == MAEST_EPI_GELU16_LN) return false;   // not instantiated for the pair kernel
   if (g_gemm_pair_mode != 2) return g_gemm_pair_mode == 1;
-  return epi == MAEST_EPI_STORE16 || epi == MAEST_EPI_STORE16_LN || (epi == MAEST_EPI_GELU16 && !has_aux) ||
+  return epi == MAEST_EPI_STORE16 || epi == MAEST_EPI_STORE16_LN || epi == MAEST_EPI_GELU16 ||
          ((epi == MAEST_EPI_RESID32 || epi == MAEST_EPI_RESID32_LN) && K >= 2048);
 }
 
 // Tensor map of the 16-bit output for the TMA-store epilogues (STORE16 / GELU16 and their LN-folded forms); set by the entry
 // points right before the dispatch, ignored by every other epilogue.
-static thread_local CUtensorMap t_tmap_c;
+static thread_local CUtensorMap t_tmap_c, t_tmap_c2;   // (second map: the saved pre-activation of GELU16_SAVE)
 
 template <int DT, int EPI>
 int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& p, cudaStream_t st) {
@@ -142,7 +142,7 @@ int launch_gemm2(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams&
   const int sms = g_num_sms[cur_device()];
   int pairs = sms / 2;
   if (pairs > num_tiles) pairs = num_tiles;
-  gemm2_tn_kernel<DT, EPI><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, t_tmap_c, p);
+  gemm2_tn_kernel<DT, EPI><<<2 * pairs, GEMM_THREADS, GEMM2_SMEM_BYTES, st>>>(ta, tb, t_tmap_c, t_tmap_c2, p);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -153,7 +153,7 @@ int launch_gemm(const CUtensorMap& ta, const CUtensorMap& tb, const GemmParams& 
   const int num_tiles = ((p.M + GEMM_BM - 1) / GEMM_BM) * ((p.N + GEMM_BN - 1) / GEMM_BN) * splits;
   const int sms = g_num_sms[cur_device()];
   const int grid = num_tiles < sms ? num_tiles : sms;
-  gemm_tn_kernel<DT, EPI, A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, t_tmap_c, p);
+  gemm_tn_kernel<DT, EPI, A_MN, B_MN><<<grid, GEMM_THREADS, GEMM_SMEM_BYTES, st>>>(ta, tb, t_tmap_c, t_tmap_c2, p);
   CUDA_OK(cudaGetLastError());
   return 0;
 }
@@ -382,8 +382,9 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   if (epilogue == MAEST_EPI_RESID32 && rows_per_group > 0) return fail(-1, "gemm: RESID32 does not support row remapping");
   if ((epilogue == MAEST_EPI_STORE16 || epilogue == MAEST_EPI_GELU16) && rows_per_group > 0) return fail(-1, "gemm: the 16-bit epilogues do not support row remapping");
   if (epilogue == MAEST_EPI_GELUBWD16 && !aux16) return fail(-1, "gemm: GELUBWD16 needs the saved pre-activation (aux16)");
-  if ((epilogue == MAEST_EPI_STORE16 || (epilogue == MAEST_EPI_GELU16 && !aux16) || epilogue == MAEST_EPI_GELUBWD16) &&
+  if ((epilogue == MAEST_EPI_STORE16 || epilogue == MAEST_EPI_GELU16 || epilogue == MAEST_EPI_GELUBWD16) &&
       (r = make_tmap(&t_tmap_c, out, op_dtype, M, N, ld_out, 32))) return r;     // TMA-store epilogue: [32 rows x 64 columns] boxes
+  if (epilogue == MAEST_EPI_GELU16 && aux16 && (r = make_tmap(&t_tmap_c2, aux16, op_dtype, M, N, ld_out, 32))) return r;
   cudaStream_t st = (cudaStream_t)stream;
   return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st)
                                 : launch_gemm_dt<DT_F16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st);

@@ -171,7 +171,7 @@ __device__ __forceinline__ float4 lds_f4(uint32_t saddr) {
 // swizzled per-warp smem tile -> row-coalesced fused epilogue.  m0 / n0: first output row / column of this warp's
 // sub-tile; `release_tmem()` is invoked once, as soon as the last accumulator column has been read.
 template <int DT, int EPI, typename ReleaseFn>
-__device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const CUtensorMap* tmap_c, uint8_t* stg, uint32_t taddr, int m0, int n0, int lane,
+__device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const CUtensorMap* tmap_c, const CUtensorMap* tmap_c2, uint8_t* stg, uint32_t taddr, int m0, int n0, int lane,
                                                       uint64_t* tfull, uint32_t aphase, ReleaseFn release_tmem) {
   using O = Op16<DT == DT_BF16 ? DT_BF16 : DT_F16>;
   const bool identity_rows = p.rows_per_group == 0x7fffffff;   // set by the host when no remap is requested
@@ -240,7 +240,9 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
   // pair mainloops run at 1580-1600 TFLOP/s; reading the accumulator out of TMEM is free; for qkv the LSU global stores were
   // 0.048 of the 0.062 ms the epilogue added (hence the TMA store), for fc1 the GELU math is 0.09 ms and the stores 0.045 ms.
   constexpr bool kPacked16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || EPI == EPI_GELU16_SAVE || kLnConsumer || EPI == EPI_GELUBWD16);
-  constexpr bool kTmaStore16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || kLnConsumer || EPI == EPI_GELUBWD16);   // single 16-bit output, no row remap
+  // 16-bit output(s) without row remap leave through the TMA store engine.  GELU16_SAVE has two (activation and saved
+  // pre-activation): both go through the ONE staging tile of the warp, one after the other.
+  constexpr bool kTmaStore16 = (EPI == EPI_STORE16 || EPI == EPI_GELU16 || kLnConsumer || EPI == EPI_GELUBWD16 || EPI == EPI_GELU16_SAVE);
   float lane_r = 0.f, lane_mr = 0.f;   // LN consumer: rstd and -mean * rstd of row m0 + lane
   if constexpr (kLnConsumer) {
     if (m0 + lane < p.M) {
@@ -269,6 +271,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
     // cc + 1 is in flight while chunk cc is processed), and the TMEM stage goes back to the MMA warp as soon as the last
     // chunk's load has completed.
     uint32_t va[32], vb[32];
+    uint32_t pre_keep[EPI == EPI_GELU16_SAVE ? 16 : 1];   // GELU16_SAVE: packed pre-activations of the even chunk, until its pair is complete
     // GELUBWD16: this thread's row of the saved pre-activation, 32 columns (64 contiguous bytes) per chunk, fetched one chunk
     // ahead like the accumulator
     uint4 ua[EPI == EPI_GELUBWD16 ? 4 : 1], ub[EPI == EPI_GELUBWD16 ? 4 : 1];
@@ -355,12 +358,37 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4)
           sts_v4(stg_s + lane * 128 + ((uint32_t(half_sel * 4 + q4) ^ uint32_t(lane & 7)) << 4), o16[4 * q4], o16[4 * q4 + 1], o16[4 * q4 + 2], o16[4 * q4 + 3]);
+        if constexpr (EPI == EPI_GELU16_SAVE) {
+          if (half_sel == 0) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q) pre_keep[q] = pre16[q];
+          }
+        }
         if (half_sel == 1 || cc == nchunks - 1) {
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
             tma_store_2d(tmap_c, stg, n - 32 * half_sel, m0);   // columns beyond N / rows beyond M are clipped
             tma_store_commit();
+          }
+          if constexpr (EPI == EPI_GELU16_SAVE) {
+            // second output through the same staging tile: wait until the store above has read it, refill with the pre-activations
+            if (lane == 0) tma_store_wait_read<0>();
+            __syncwarp();
+            if (half_sel == 1) {
+#pragma unroll
+              for (int q4 = 0; q4 < 4; ++q4)
+                sts_v4(stg_s + lane * 128 + ((uint32_t(q4) ^ uint32_t(lane & 7)) << 4), pre_keep[4 * q4], pre_keep[4 * q4 + 1], pre_keep[4 * q4 + 2], pre_keep[4 * q4 + 3]);
+            }
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4)
+              sts_v4(stg_s + lane * 128 + ((uint32_t(half_sel * 4 + q4) ^ uint32_t(lane & 7)) << 4), pre16[4 * q4], pre16[4 * q4 + 1], pre16[4 * q4 + 2], pre16[4 * q4 + 3]);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(tmap_c2, stg, n - 32 * half_sel, m0);
+              tma_store_commit();
+            }
           }
         }
         return;
@@ -502,7 +530,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
 template <int DT, int EPI, bool A_MN = false, bool B_MN = false>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-               const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+               const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg_base = smem + GEMM_STAGES * GEMM_STAGE_BYTES;
@@ -623,7 +651,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant
       const int m0 = (tile / num_n) * GEMM_BM + q * 32;
       const int n0 = (tile % num_n) * GEMM_BN + half * 128;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN + half * 128);
-      gemm_epilogue_subtile<DT, EPI>(p, &tmap_c, stg, taddr, m0, n0, lane, &tfull_bar[as], aphase, [&]() { mbar_arrive(&tempty_bar[as]); });
+      gemm_epilogue_subtile<DT, EPI>(p, &tmap_c, &tmap_c2, stg, taddr, m0, n0, lane, &tfull_bar[as], aphase, [&]() { mbar_arrive(&tempty_bar[as]); });
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
     if (lane == 0) tma_store_wait<0>();   // bulk stores of this warp (TMA-store epilogues) have landed before the CTA exits

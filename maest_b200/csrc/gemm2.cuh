@@ -18,7 +18,7 @@ constexpr int GEMM2_SMEM_BYTES = GEMM2_STAGES * GEMM2_STAGE_BYTES + GEMM_EPI_WAR
 template <int DT, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GEMM_THREADS, 1)
 gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                const __grid_constant__ CUtensorMap tmap_c, const GemmParams p) {
+                const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2, const GemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* stg_base = smem + GEMM2_STAGES * GEMM2_STAGE_BYTES;
@@ -116,7 +116,7 @@ gemm2_tn_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constan
       const int m0 = (t / num_n) * 256 + int(rank) * 128 + q * 32;
       const int n0 = (t % num_n) * GEMM_BN + half * 128;
       const uint32_t taddr = tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * GEMM_BN + half * 128);
-      gemm_epilogue_subtile<DT, EPI>(p, &tmap_c, stg, taddr, m0, n0, lane, &tfull_bar[as], aphase,
+      gemm_epilogue_subtile<DT, EPI>(p, &tmap_c, &tmap_c2, stg, taddr, m0, n0, lane, &tfull_bar[as], aphase,
                                      [&]() { mbar_arrive_cluster(&tempty_bar[as], 0); });
       if (++as == 2) { as = 0; aphase ^= 1; }
     }
