@@ -328,6 +328,7 @@ def train_leg(args, steps: int, warmup: int, B: int):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     clocks = sampler.stop() if rank == 0 else None
+    ar_mode = getattr(net, "grad_allreduce", None)
     ar_ms = [a.elapsed_time(b) for a, b in net.allreduce_events]
     ar_ms = sum(ar_ms) / len(ar_ms) if ar_ms else 0.0
     if world > 1:
@@ -347,8 +348,8 @@ def train_leg(args, steps: int, warmup: int, B: int):
                     config=dict(workload=f"maest_30s_from_passt_pretrain training step: mel [{B},1,96,1875] fp16 per GPU, s_patchout_t=90 -> {N} tokens, "
                                          "mixup 0.3, BCE, fwd+bwd" + (" + NCCL gradient all-reduce" if world > 1 else "") + " + AdamW step",
                                 batch_per_gpu=B, tokens=N, gflop_per_clip_fwd=fl["total"] / 1e9),
-                    loss=float(loss.detach()), grad_elements_allreduced=n_grad[0], allreduce_bytes=(2 if net.grad_allreduce == "bf16" else 4) * n_grad[0],
-                    allreduce_ms_exposed=ar_ms, allreduce=("one flat " + ("bf16-compressed" if net.grad_allreduce == "bf16" else "fp32") +
+                    loss=float(loss.detach()), grad_elements_allreduced=n_grad[0], allreduce_bytes=(2 if ar_mode == "bf16" else 4) * n_grad[0],
+                    allreduce_ms_exposed=ar_ms, allreduce=("one flat " + ("bf16-compressed" if ar_mode == "bf16" else "fp32") +
                                " dist.all_reduce (NCCL) after the last backward kernel, not overlapped") if world > 1 else "none (1 GPU)",
                     clocks=clocks,
                     model_tflops=tf, model_frac_of_bf16_sustained=tf / peaks["bf16_tflops_sustained"],
