@@ -53,7 +53,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   uint64_t* sdp_full = bars + 5;     // S_i, dP_i in TMEM
   uint64_t* pds_full = bars + 6;     // P_i, dS_i in smem (count 128)
   uint64_t* mma2_done = bars + 7;    // dV/dK/dQ GEMMs of iteration i retired
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* sdp_free = bars + 8;     // every compute warp has S_i / dP_i in registers: the TMEM buffers may take S_{i+1} / dP_{i+1}
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int kv0 = blockIdx.x * 128;
@@ -71,6 +72,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     mbar_init(sdp_full, 1);
     mbar_init(pds_full, ATTB_CWARPS * 32);
     mbar_init(mma2_done, 2);
+    mbar_init(sdp_free, ATTB_CWARPS);
     fence_mbar_init();
   }
   if (warp == ATTB_CWARPS) {
@@ -123,13 +125,16 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       for (int i = 0; i < nq; ++i) {
         int nstage = stage ^ 1;
         uint32_t nphase = stage == 1 ? phase ^ 1 : phase;
-        mbar_wait(pds_full, i & 1);
-        tc_fence_after();
+        // S / dP of the NEXT query tile go out as soon as the compute warps have read this one's out of TMEM -- not after their
+        // whole P / dS phase (r02 clocks: the compute warps then idled 1900 of 4850 cycles per iteration waiting for the scores)
         if (i + 1 < nq) {
+          mbar_wait(sdp_free, i & 1);
           mbar_wait(&qdo_full[nstage], nphase);
           tc_fence_after();
           issue_s_dp(nstage);
         }
+        mbar_wait(pds_full, i & 1);
+        tc_fence_after();
         const uint32_t aO = smem_u32(sdO + stage * ATT_TILE_BYTES);
 #pragma unroll
         for (int k = 0; k < 8; ++k)   // dV[key, d] += sum_q P[q, key] dO[q, d]
@@ -203,7 +208,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       }
 #endif
     };
+#ifdef ATTB_DIAG
+    unsigned dg_wait_s = 0, dg_math = 0, dg_wait_mma = 0, dg_drain = 0, dg_store = 0, dg_arrive = 0;
+    const long long dg_start = clock64();
+#define DG(var) do { const unsigned n__ = (unsigned)clock(); var += n__ - dg_t; dg_t = n__; } while (0)
+#else
+#define DG(var) do { } while (0)
+#endif
     for (int i = 0; i < nq; ++i) {
+#ifdef ATTB_DIAG
+      unsigned dg_t = (unsigned)clock();
+#endif
       const int qrow = i * 128 + row;
       const bool q_ok = qrow < p.N;
       const float lse2 = q_ok ? p.lse[stat_base + qrow] : 0.f;
@@ -211,12 +226,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       const bool full_tile = (kv0 + 128 <= p.N) && (i * 128 + 128 <= p.N);     // CTA-uniform
       mbar_wait(sdp_full, i & 1);
       tc_fence_after();
+      DG(dg_wait_s);
 #pragma unroll 1
       for (int c = 2 * wg; c < 2 * wg + 2; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld32(tS + lane_off + uint32_t(c * 32), sv);
         tmem_ld32(tdP + lane_off + uint32_t(c * 32), dv);
         tc_wait_ld();
+        if (c == 2 * wg + 1) {       // this warp's last chunk of S_i / dP_i is in registers
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(sdp_free);
+        }
         uint32_t pkP[16], pkD[16];
         // only the clip's last key tile and last query tile have rows / keys to mask: everywhere else the per-element
         // compare + select pairs (30 % of this kernel's instructions, r02c_prof_attention_bwd) are skipped
@@ -244,10 +265,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
             pkD[k >> 1] = O16::pack(d0, d1);
           }
         }
+        DG(dg_math);
         if (c == 2 * wg && i > 0) {   // the previous iteration's GEMMs must retire before P/dS smem is overwritten
           mbar_wait(mma2_done, (i - 1) & 1);
           tc_fence_after();
+          DG(dg_wait_mma);
           drain_dq(i - 1);
+          DG(dg_drain);
         }
         uint8_t* bp = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
         uint8_t* bd = sdS + (c >> 1) * ATT_TILE_BYTES + row * 128;
@@ -257,11 +281,18 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           *reinterpret_cast<uint4*>(bp + chunk) = make_uint4(pkP[4 * q4], pkP[4 * q4 + 1], pkP[4 * q4 + 2], pkP[4 * q4 + 3]);
           *reinterpret_cast<uint4*>(bd + chunk) = make_uint4(pkD[4 * q4], pkD[4 * q4 + 1], pkD[4 * q4 + 2], pkD[4 * q4 + 3]);
         }
+        DG(dg_store);
       }
       fence_proxy_async_smem();
       tc_fence_before();
       mbar_arrive(pds_full);
+      DG(dg_arrive);
     }
+#ifdef ATTB_DIAG
+    if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 0 || threadIdx.x == 128))
+      printf("ATTB_DIAG wg %d nq %d per-iteration cycles: wait_s %u math %u wait_mma2 %u drain %u store %u fence+arrive %u | loop total %lld\n", wg, nq,
+             dg_wait_s / nq, dg_math / nq, dg_wait_mma / nq, dg_drain / nq, dg_store / nq, dg_arrive / nq, (clock64() - dg_start) / nq);
+#endif
     mbar_wait(mma2_done, (nq - 1) & 1);
     tc_fence_after();
     drain_dq(nq - 1);
