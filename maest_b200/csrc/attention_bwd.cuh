@@ -20,7 +20,13 @@
 
 namespace mb {
 
-constexpr int ATTB_CWARPS = 8;                      // compute warps (two warpgroups)
+#ifndef ATTB_COMPUTE_WARPS
+#define ATTB_COMPUTE_WARPS 16
+#endif
+constexpr int ATTB_CWARPS = ATTB_COMPUTE_WARPS;      // compute warps: 8 (two warpgroups, two 32-key chunks each) or 16 (four, one each)
+constexpr int ATTB_NWG = ATTB_CWARPS / 4;
+constexpr int ATTB_CPW = 4 / ATTB_NWG;               // 32-key chunks of a row per warpgroup
+static_assert(ATTB_CWARPS == 8 || ATTB_CWARPS == 16, "two or four compute warpgroups");
 constexpr int ATTB_THREADS = (ATTB_CWARPS + 3) * 32; // + TMA warp + two MMA-issuing warps
 constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 12 + 128;   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves), dQ staging (2 x [128 x 32] fp32)
 
@@ -187,7 +193,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     auto drain_dq = [&](int i) {
       if (threadIdx.x == 0) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tile
       compute_bar();
-      {
+      if constexpr (ATTB_NWG == 2) {
         const int c = wg;
         uint32_t v[32];
         tmem_ld32(tdQ + lane_off + uint32_t(c * 32), v);
@@ -196,6 +202,14 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
 #pragma unroll
         for (int q4 = 0; q4 < 8; ++q4)
           *reinterpret_cast<uint4*>(base + ((q4 ^ (row & 7)) << 4)) = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+      } else {      // four warpgroups: 16 of the 64 dQ columns each = half of a [128 x 32] fp32 staging tile
+        uint32_t v[16];
+        tmem_ld16(tdQ + lane_off + uint32_t(wg * 16), v);
+        tc_wait_ld();
+        uint8_t* base = sdQ + (wg >> 1) * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4)
+          *reinterpret_cast<uint4*>(base + (((4 * (wg & 1) + q4) ^ (row & 7)) << 4)) = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
       }
       fence_proxy_async_smem();
       tc_fence_before();
@@ -228,12 +242,12 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       tc_fence_after();
       DG(dg_wait_s);
 #pragma unroll 1
-      for (int c = 2 * wg; c < 2 * wg + 2; ++c) {
+      for (int c = ATTB_CPW * wg; c < ATTB_CPW * wg + ATTB_CPW; ++c) {
         uint32_t sv[32], dv[32];
         tmem_ld32(tS + lane_off + uint32_t(c * 32), sv);
         tmem_ld32(tdP + lane_off + uint32_t(c * 32), dv);
         tc_wait_ld();
-        if (c == 2 * wg + 1) {       // this warp's last chunk of S_i / dP_i is in registers
+        if (c == ATTB_CPW * wg + ATTB_CPW - 1) {       // this warp's last chunk of S_i / dP_i is in registers
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(sdp_free);
@@ -266,7 +280,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           }
         }
         DG(dg_math);
-        if (c == 2 * wg && i > 0) {   // the previous iteration's GEMMs must retire before P/dS smem is overwritten
+        if (c == ATTB_CPW * wg && i > 0) {   // the previous iteration's GEMMs must retire before P/dS smem is overwritten
           mbar_wait(mma2_done, (i - 1) & 1);
           tc_fence_after();
           DG(dg_wait_mma);
@@ -300,9 +314,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     const int key = kv0 + row;
     typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.dqkv16) + long(row_base + key) * (3 * p.H * 64) + h * 64;
     {
-      const int which = wg;                     // 0: dK -> column block 1, 1: dV -> column block 2
+      // two warpgroups: one takes dK, the other dV; four: (dK | dV) x (columns 0-31 | 32-63)
+      const int which = ATTB_NWG == 2 ? wg : (wg >> 1);     // 0: dK -> column block 1, 1: dV -> column block 2
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
+      for (int c = (ATTB_NWG == 2 ? 0 : (wg & 1)); c < (ATTB_NWG == 2 ? 2 : (wg & 1) + 1); ++c) {
         uint32_t v[32];
         tmem_ld32((which ? tdV : tdK) + lane_off + uint32_t(c * 32), v);
         tc_wait_ld();
