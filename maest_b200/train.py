@@ -31,6 +31,11 @@ class MaestTrainStep(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, model, mel, targets, keep_ft, t_offset, *params):
+        with ops.launch_scope(mel.device):
+            return MaestTrainStep._forward(ctx, model, mel, targets, keep_ft, t_offset, *params)
+
+    @staticmethod
+    def _forward(ctx, model, mel, targets, keep_ft, t_offset, *params):
         dt = model.op_dtype
         dev = mel.device
         names = [n for n, _ in _flat_params(model)]
@@ -92,6 +97,11 @@ class MaestTrainStep(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, dloss, *_unused):
+        with ops.launch_scope(dloss.device):
+            return MaestTrainStep._backward(ctx, dloss, *_unused)
+
+    @staticmethod
+    def _backward(ctx, dloss, *_unused):
         model, names, P_ = ctx.model, ctx.names, ctx.params
         dt = model.op_dtype
         B, N, P, T, t_off = ctx.dims
@@ -253,17 +263,18 @@ def training_forward(model, mel: torch.Tensor, targets, mix: Optional[tuple] = N
     dev = model.cls_token.device
     if dev.type != "cuda":
         raise RuntimeError("maest_b200: training runs on CUDA (B200) only")
-    mel = mel.to(dev)
-    targets = tuple(t.to(dev) for t in targets) if sep else targets.to(dev)
+    mel = ops.h2d(mel, dev)
+    targets = tuple(ops.h2d(t, dev) for t in targets) if sep else ops.h2d(targets, dev)
     if mel.dim() == 4:
         mel = mel[:, 0]
     if mix is not None:
         perm, lam = mix
-        mel = ops.mixup(mel, perm.to(dev), lam.to(dev))
+        perm_d, lam_d = ops.h2d(perm.to(torch.int32), dev), ops.h2d(lam.float(), dev)
+        mel = ops.mixup(mel, perm_d, lam_d)
         if sep:
-            targets = tuple(ops.mixup(t, perm.to(dev), lam.to(dev)) for t in targets)
+            targets = tuple(ops.mixup(t, perm_d, lam_d) for t in targets)
         else:
-            targets = ops.mixup(targets, perm.to(dev), lam.to(dev))
+            targets = ops.mixup(targets, perm_d, lam_d)
     if mel.shape[1] != 96:
         raise NotImplementedError(f"the B200 patch kernels take 96 mel bands, got {mel.shape[1]}")
     Fp, Tp = (mel.shape[1] - 16) // 10 + 1, (mel.shape[2] - 16) // 10 + 1
