@@ -353,7 +353,7 @@ def train_leg(args, steps: int, warmup: int, B: int):
                                " dist.all_reduce (NCCL) after the last backward kernel, not overlapped") if world > 1 else "none (1 GPU)",
                     clocks=clocks,
                     model_tflops=tf, model_frac_of_bf16_sustained=tf / peaks["bf16_tflops_sustained"],
-                    gpu_launches=steps * (12 * 30 + 12))
+                    gpu_launches=steps * 333)      # mb:: kernels per step (profiles/r02d_launches_train_step.txt)
     del mod, net, opt
     torch.cuda.empty_cache()
     return line
