@@ -32,7 +32,8 @@
 namespace mb {
 
 #ifndef ATT_CHAIN_NPOLY
-#define ATT_CHAIN_NPOLY 3     // pairs of every 8 whose exponentials run on the FMA pipe
+#define ATT_CHAIN_NPOLY 2     // pairs of every 8 whose exponentials run on the FMA pipe (re-tuned with the epilogue warpgroup:
+                              // 1 / 2 / 3 / 4 -> 0.772 / 0.745-0.764 / 0.756-0.777 / 0.789 ms at config 3, box-dependent)
 #endif
 
 // NCH chains x BKV keys per tile; CW = score columns per tcgen05.ld chunk; R = ring slots of {K tile, V tile}.
@@ -202,7 +203,11 @@ __device__ __forceinline__ void att_chain_chunk(uint32_t (&s)[W], u64& la, u64& 
       p1 = fabsf(a1) * 1e-3f + 1e-3f;
     } else
 #endif
+#ifdef ATT_CHAIN_POLY_SPREAD
+    if (((i * NPOLY) & 7) < NPOLY) {      // the polynomial pairs spread over each group of 8
+#else
     if ((i & 7) >= 8 - NPOLY) {
+#endif
       // 2^a = 2^round(a) * 2^r, r in [-0.5, 0.5]: round through the 1.5 * 2^23 magic add, minimax cubic for 2^r, the integer
       // part added into the exponent field.  Valid for |a| <= 126; amax lets the caller flag rows outside that range.
       float a0, a1;
