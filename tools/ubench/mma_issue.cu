@@ -17,7 +17,9 @@ using namespace mb;
 
 #define G 512
 
-template <int N, int NM, int TS, int WARPS>
+// ALT = 1: consecutive MMAs of a group alternate between TWO accumulators (independent chains): separates the per-instruction
+// issue cost from the latency of a chain of MMAs that accumulate into the same TMEM tile.
+template <int N, int NM, int TS, int WARPS, int ALT = 0>
 __global__ void bench(long long* out) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[8];
@@ -41,8 +43,10 @@ __global__ void bench(long long* out) {
     for (int g = 0; g < G; ++g) {
 #pragma unroll
       for (int k = 0; k < NM; ++k) {
-        if (TS) mma_ts(d, tb + 256 + 8 * (k & 7), bd + 2 * (k & 3), idesc, k ? 1u : 0u);
-        else mma_ss(d, ad + 2 * (k & 3), bd + 2 * (k & 3), idesc, k ? 1u : 0u);
+        const uint32_t dk = ALT ? d + uint32_t((k & 1) * 64) : d;
+        const uint32_t acc = ALT ? (k > 1 ? 1u : 0u) : (k ? 1u : 0u);
+        if (TS) mma_ts(dk, tb + 256 + 8 * (k & 7), bd + 2 * (k & 3), idesc, acc);
+        else mma_ss(dk, ad + 2 * (k & 3), bd + 2 * (k & 3), idesc, acc);
       }
       tc_commit(&bars[warp * 2 + (g & 1)]);
     }
@@ -59,11 +63,11 @@ __global__ void bench(long long* out) {
   if (warp == 0) { tc_fence_after(); tmem_dealloc<512>(tb); }
 }
 
-template <int N, int NM, int TS, int WARPS>
+template <int N, int NM, int TS, int WARPS, int ALT = 0>
 void run(const char* name) {
   long long* out; cudaMalloc(&out, 148 * 8 * 8); cudaMemset(out, 0, 148 * 8 * 8);
-  cudaFuncSetAttribute(bench<N, NM, TS, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
-  for (int r = 0; r < 2; ++r) { bench<N, NM, TS, WARPS><<<148, 128, 65536>>>(out); cudaDeviceSynchronize(); }
+  cudaFuncSetAttribute(bench<N, NM, TS, WARPS, ALT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  for (int r = 0; r < 2; ++r) { bench<N, NM, TS, WARPS, ALT><<<148, 128, 65536>>>(out); cudaDeviceSynchronize(); }
   long long h[148 * 8]; cudaMemcpy(h, out, sizeof(h), cudaMemcpyDeviceToHost);
   double ti = 0, ta = 0; for (int b = 0; b < 148; ++b) { ti += h[b * 8]; ta += h[b * 8 + 1]; }
   cudaError_t e = cudaGetLastError();
@@ -82,6 +86,8 @@ int main() {
   run<256, 1, 0, 1>("SS N=256 x1 + commit");
   run<128, 4, 0, 2>("SS N=128 x4 + commit, two issuing warps");
   run<64, 4, 1, 2>("TS N=64  x4 + commit, two issuing warps");
+  run<64, 8, 1, 1, 1>("TS N=64  x8 + commit, alternating two accumulators");
+  run<64, 8, 0, 1, 1>("SS N=64  x8 + commit, alternating two accumulators");
   run<32, 4, 0, 1>("SS N=32  x4 + commit");
   run<16, 4, 0, 1>("SS N=16  x4 + commit");
   return 0;
