@@ -211,7 +211,7 @@ def kernel_breakdown(model, wav, iters: int = 3):
         h, qkv, o, u = bufs["h"], bufs["qkv"], bufs["o"], bufs["u"]
         stats = parts = None
         if fuse:
-            parts = torch.empty((EMBED // 32, M, 4), device=dev, dtype=torch.float32)
+            parts = torch.empty((EMBED // 128, M, 4), device=dev, dtype=torch.float32)
         for i, blk in enumerate(model.blocks):
             w = {k: model._weight16(f"blocks.{i}.{k}", p) for k, p in (("qkv", blk.attn.qkv.weight), ("proj", blk.attn.proj.weight),
                                                                        ("fc1", blk.mlp.fc1.weight), ("fc2", blk.mlp.fc2.weight))}

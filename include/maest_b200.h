@@ -189,7 +189,7 @@ int32_t maest_ln_fold(const void* w16, const float* gamma, const float* beta, co
 
 /* Linear layers with the neighbouring LayerNorm folded in (epilogue = MAEST_EPI_*_LN).
  *   producer (RESID32_LN): out32 = resid + A W^T + bias;  out16b = out32 * ln_vec (gamma of the next LayerNorm);
- *                          ln_stats = partials fp32 [N/32, M, 4]: (pivot, sum (x - pivot), sum (x - pivot)^2, unused) of every
+ *                          ln_stats = partials fp32 [N/128, M, 4]: (pivot, sum (x - pivot), sum (x - pivot)^2, feature count) of every
  *                          32-column chunk of the new rows -- plain stores, no atomics, bit-reproducible
  *   maest_ln_finalize:     partials -> stats fp32 [M, 2] = (rstd, -mean * rstd)
  *   consumer (STORE16_LN / GELU16_LN): A = the producer's out16b; ln_stats = stats; ln_vec = wg, bias = bf from maest_ln_fold */

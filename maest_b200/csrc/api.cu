@@ -126,9 +126,8 @@ int g_gemm_pair_mode = 2;   // 0: 1-CTA tiles, 1: CTA-pair (cta_group::2) tiles,
 // and, with the packed / TMA-store epilogue, for the inference fc1 + GELU (0.476 -> 0.450 ms); it loses for proj (0.188 -> 0.197 ms)
 // and, once both of its outputs left through TMA stores, also for the training forward fc1 (GELU16_SAVE).
 inline bool use_pair_kernel(int epi, int K, bool has_aux = false) {
-  if (epi == MAEST_EPI_GELU16_LN) return false;   // not instantiated for the pair kernel
   if (g_gemm_pair_mode != 2) return g_gemm_pair_mode == 1;
-  return epi == MAEST_EPI_STORE16 || epi == MAEST_EPI_STORE16_LN || epi == MAEST_EPI_GELU16 ||
+  return epi == MAEST_EPI_STORE16 || epi == MAEST_EPI_STORE16_LN || epi == MAEST_EPI_GELU16 || epi == MAEST_EPI_GELU16_LN ||
          ((epi == MAEST_EPI_RESID32 || epi == MAEST_EPI_RESID32_LN) && K >= 2048);
 }
 
@@ -170,6 +169,7 @@ int launch_gemm_dt(int epi, bool a_mn, bool b_mn, const CUtensorMap& ta, const C
       case MAEST_EPI_RESID32: return launch_gemm2<DT, EPI_RESID32>(ta, tb, p, st);
       case MAEST_EPI_STORE32: return launch_gemm2<DT, EPI_STORE32>(ta, tb, p, st);
       case MAEST_EPI_STORE16_LN: return launch_gemm2<DT, EPI_STORE16_LN>(ta, tb, p, st);
+      case MAEST_EPI_GELU16_LN: return launch_gemm2<DT, EPI_GELU16_LN>(ta, tb, p, st);
       case MAEST_EPI_RESID32_LN: return launch_gemm2<DT, EPI_RESID32_LN>(ta, tb, p, st);
     }
   }
@@ -221,6 +221,7 @@ int init_dt() {
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_RESID32>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_STORE32>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_STORE16_LN>, GEMM2_SMEM_BYTES))) return r;
+  if ((r = set_smem(gemm2_tn_kernel<DT, EPI_GELU16_LN>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm2_tn_kernel<DT, EPI_RESID32_LN>, GEMM2_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_STORE16_LN, false, false>, GEMM_SMEM_BYTES))) return r;
   if ((r = set_smem(gemm_tn_kernel<DT, EPI_GELU16_LN, false, false>, GEMM_SMEM_BYTES))) return r;
@@ -413,8 +414,8 @@ int32_t maest_ln_fold(const void* w16, const float* gamma, const float* beta, co
 
 int32_t maest_ln_finalize(const float* partials, int32_t rows, int32_t n_features, float eps, float* stats, void* stream) {
   if (rows <= 0) return 0;
-  if (n_features % 32) return fail(-1, "ln_finalize: n_features %% 32 must be 0");
-  ln_finalize_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(partials), rows, rows, n_features / 32, eps,
+  if (n_features % GEMM_LN_PART) return fail(-1, "ln_finalize: n_features %% %d must be 0", GEMM_LN_PART);
+  ln_finalize_kernel<<<(rows + 255) / 256, 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<const float4*>(partials), rows, rows, n_features / GEMM_LN_PART, eps,
                                                                              reinterpret_cast<float2*>(stats));
   CUDA_OK(cudaGetLastError());
   return 0;

@@ -21,6 +21,7 @@ constexpr int GEMM_STAGES = 4;
 constexpr int GEMM_THREADS = 384;
 constexpr int GEMM_EPI_WARPS = 8;
 constexpr int GEMM_STG_BYTES = 32 * 32 * 4;        // per-epilogue-warp staging tile: 32 rows x 32 fp32
+constexpr int GEMM_LN_PART = 128;                  // LayerNorm folding: features per row-statistics partial (= columns per epilogue warp)
 constexpr int GEMM_A_BYTES = GEMM_BM * GEMM_BK * 2;  // 16 KB
 constexpr int GEMM_B_BYTES = GEMM_BN * GEMM_BK * 2;  // 32 KB
 constexpr int GEMM_STAGE_BYTES = GEMM_A_BYTES + GEMM_B_BYTES;
@@ -440,6 +441,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
     }
     return;
   }
+  float ln_pv[kLnProducer ? 8 : 1], ln_s1[kLnProducer ? 8 : 1], ln_s2[kLnProducer ? 8 : 1];
 #pragma unroll 1
   for (int cc = 0; cc < nchunks; ++cc) {
     const int n = n0 + cc * 32;
@@ -471,25 +473,38 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
     }
     if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) load_resid(cc + 1);   // next chunk's residual / table rows are in flight during the stores
     if constexpr (kLnProducer) {
-      // row statistics of the new residual stream, per 32-column chunk, about a pivot (the chunk's first element, broadcast
-      // inside the 8 lanes that share a row) so that a large common offset of the row does not cancel: one broadcast + one
-      // 3-step butterfly carrying (sum d, sum d^2), d = x - pivot; ln_finalize_kernel merges the chunks.  All lanes take part
-      // in the shuffles (rows beyond M are not stored).  Partials are laid out [chunk][row] so the merge reads are coalesced.
-      const int chunk = n >> 5;
+      // Row statistics of the new residual stream over THIS WARP'S 128 columns (GEMM_LN_PART), about a pivot (the first element of
+      // the row in the warp's first chunk, broadcast inside the 8 lanes that share a row) so that a large common offset of the
+      // row does not cancel.  Every lane accumulates (sum d, sum d^2), d = x - pivot, over its 4 columns of all four chunks in
+      // registers; ONE 3-step butterfly per row after the last chunk (it was one per 32-column chunk: 224 shuffles per sub-tile
+      // and thread instead of 56 -- the folded proj epilogue took 0.40 ms against 0.20 ms for the plain one).
+      // ln_finalize_kernel merges the N / 128 partials of a row.  Partials are laid out [part][row]: coalesced merge reads.
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 a = acc4[i];
-        const float pv = __shfl_sync(0xffffffffu, a.x, lane & ~7);
-        const float dx = a.x - pv, dy = a.y - pv, dz = a.z - pv, dw = a.w - pv;
-        float s1 = (dx + dy) + (dz + dw);
-        float s2 = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, dw * dw)));
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-          s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+        if (cc == 0) {
+          ln_pv[i] = __shfl_sync(0xffffffffu, a.x, lane & ~7);
+          ln_s1[i] = 0.f;
+          ln_s2[i] = 0.f;
         }
-        if (row_ok(i) && c4 == 0)
-          *reinterpret_cast<float4*>(p.ln_stats + (long(chunk) * p.ln_rows + out_row(i)) * 4) = make_float4(pv, s1, s2, 0.f);
+        const float pv = ln_pv[i];
+        const float dx = a.x - pv, dy = a.y - pv, dz = a.z - pv, dw = a.w - pv;
+        ln_s1[i] += (dx + dy) + (dz + dw);
+        ln_s2[i] = fmaf(dx, dx, fmaf(dy, dy, fmaf(dz, dz, fmaf(dw, dw, ln_s2[i]))));
+      }
+      if (cc == nchunks - 1) {
+        const int part = n0 / GEMM_LN_PART;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float s1 = ln_s1[i], s2 = ln_s2[i];
+#pragma unroll
+          for (int o = 1; o < 8; o <<= 1) {
+            s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+            s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+          }
+          if (row_ok(i) && c4 == 0)
+            *reinterpret_cast<float4*>(p.ln_stats + (long(part) * p.ln_rows + out_row(i)) * 4) = make_float4(ln_pv[i], s1, s2, float(32 * nchunks));
+        }
       }
     }
 #pragma unroll

@@ -69,8 +69,8 @@ __global__ void __launch_bounds__(256) ln_fold_kernel(const void* __restrict__ w
   if (lane == 0) { wg[n] = a; bf[n] = (bias ? bias[n] : 0.f) + b; }
 }
 
-// LayerNorm folding, statistics side: merge the per-chunk partials (pivot, sum d, sum d^2 with d = x - pivot; 32 features per
-// chunk) written by the producer GEMM epilogue into (rstd, -mean * rstd) per row (pairwise update of Chan et al., fixed order).
+// LayerNorm folding, statistics side: merge the partials (pivot, sum d, sum d^2 with d = x - pivot, number of features; 128
+// features per partial) written by the producer GEMM epilogue into (rstd, -mean * rstd) per row (pairwise update of Chan et al., fixed order).
 // Partials are [chunk][rows]: consecutive threads read consecutive 16-byte records.
 __global__ void __launch_bounds__(256) ln_finalize_kernel(const float4* __restrict__ part, int rows, long row_pitch, int nparts, float eps,
                                                           float2* __restrict__ stats) {
@@ -80,12 +80,13 @@ __global__ void __launch_bounds__(256) ln_finalize_kernel(const float4* __restri
 #pragma unroll 8
   for (int c = 0; c < nparts; ++c) {
     const float4 q = __ldg(part + long(c) * row_pitch + row);
-    const float mc = q.x + q.y * (1.0f / 32.0f);               // chunk mean
-    const float m2c = fmaxf(q.z - q.y * q.y * (1.0f / 32.0f), 0.f);   // chunk sum of squared deviations from its mean
-    const float tot = cnt + 32.0f;
+    const float nc = q.w, inv = 1.0f / q.w;
+    const float mc = q.x + q.y * inv;                          // partial mean
+    const float m2c = fmaxf(q.z - q.y * q.y * inv, 0.f);       // partial sum of squared deviations from its mean
+    const float tot = cnt + nc;
     const float d = mc - mean;
-    mean += d * (32.0f / tot);
-    m2 += m2c + d * d * (cnt * 32.0f / tot);
+    mean += d * (nc / tot);
+    m2 += m2c + d * d * (cnt * nc / tot);
     cnt = tot;
   }
   const float rstd = rsqrtf(m2 / cnt + eps);

@@ -229,7 +229,8 @@ class MAEST(nn.Module):
         self.attn_variant = attn_variant
         # inference option: fold norm1 / norm2 into the GEMM epilogues around them (23 of 24 LayerNorm launches disappear).
         # Off by default: measured on B200 at config 3 the heavier proj / fc2 / qkv epilogues cost what the LayerNorm kernels
-        # saved (1964 vs 1979 clips/s, profiles/README.md); results are bit-reproducible either way.
+        # save (round 1: 1964 vs 1979 clips/s; round 2 after the statistics rework: 2121-2132 vs 2114-2116);
+        # results are bit-reproducible either way.
         self.fuse_ln = fuse_ln
         if num_classes == 400:
             self.labels = discogs_400labels

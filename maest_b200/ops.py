@@ -267,7 +267,7 @@ def ln_finalize(partials: torch.Tensor, eps: float = 1e-6) -> torch.Tensor:
     stats = torch.empty((M, 2), device=partials.device, dtype=torch.float32)
     with _dev(partials.device):
         lib = _lib_for(partials)
-        _lib.check(lib.maest_ln_finalize(partials.data_ptr(), M, nparts * 32, float(eps), stats.data_ptr(), _stream()), "ln_finalize")
+        _lib.check(lib.maest_ln_finalize(partials.data_ptr(), M, nparts * 128, float(eps), stats.data_ptr(), _stream()), "ln_finalize")
     return stats
 
 

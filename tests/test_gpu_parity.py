@@ -281,7 +281,7 @@ def test_layernorm_folding_units():
     gamma, beta = (1 + 0.3 * torch.randn(D, generator=g)).cuda(), (0.2 * torch.randn(D, generator=g)).cuda()
     w2 = (torch.randn(N2, D, generator=g) * 0.04).half().cuda()
     b2 = torch.randn(N2, generator=g).cuda() * 0.1
-    parts = torch.full((D // 32, M, 4), float("nan"), device="cuda")
+    parts = torch.full((D // 128, M, 4), float("nan"), device="cuda")
     h16 = torch.empty(M, D, device="cuda", dtype=torch.float16)
     x1 = ops.linear_ln(a, wp, bp, _lib.EPI_RESID32_LN, parts, gamma, resid=x0, out16b=h16)
     ref_x1 = x0.double() + a.double() @ wp.double().t() + bp.double()
