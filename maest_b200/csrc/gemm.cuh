@@ -206,9 +206,9 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
     if constexpr (kRemap) return orow_[i];
     return long(m0 + i * 4 + sub_row);
   };
-  float4 xr[8];
-  uint2 ar[8];   // GELUBWD16: the saved pre-activation tile, prefetched the same way
-  auto load_resid = [&](int cc) {
+  float4 xr[8], xn[8];   // residual / table rows of the current chunk and of the next one (two chunks of loads in flight)
+  uint2 ar[8];   // (unused since GELUBWD16 moved to the TMEM-layout path)
+  auto load_resid_to = [&](float4 (&xr)[8], int cc) {
     if constexpr (EPI == EPI_RESID32 || EPI == EPI_RESID32_LN) {
       const int col = n0 + cc * 32 + c4 * 4;
 #pragma unroll
@@ -234,6 +234,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
       }
     }
   };
+  auto load_resid = [&](int cc) { load_resid_to(xr, cc); };
   constexpr bool kLnConsumer = (EPI == EPI_STORE16_LN || EPI == EPI_GELU16_LN);
   constexpr bool kLnProducer = (EPI == EPI_RESID32_LN);
   // 16-bit-output epilogues do their math in the TMEM-load layout (lane = row) and transpose the PACKED 16-bit tile (half the
@@ -453,6 +454,10 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
       __syncwarp();
       if (lane == 0) release_tmem();   // one arrival per warp: 8 (16 for a CTA pair, half of them remote) instead of 256 (512)
     }
+    // the NEXT chunk's residual / table rows are requested before this chunk is touched: two chunks of global loads in flight per
+    // thread (the HBM-bound proj GEMM ran at 4.2 TB/s with one: the loads issued after chunk cc's arithmetic were not back
+    // when chunk cc + 1 needed them)
+    if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) load_resid_to(xn, cc + 1);
     __syncwarp();              // previous chunk's staging reads are complete
 #pragma unroll
     for (int j = 0; j < 8; ++j) sts_v4(stg_s + lane * 128 + ((j ^ (lane & 7)) << 4), v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -471,7 +476,10 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
       if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) { a.x += xr[i].x; a.y += xr[i].y; a.z += xr[i].z; a.w += xr[i].w; }
       acc4[i] = a;
     }
-    if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) load_resid(cc + 1);   // next chunk's residual / table rows are in flight during the stores
+    if constexpr (EPI == EPI_RESID32 || EPI == EPI_STORE32 || kLnProducer) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) xr[i] = xn[i];
+    }
     if constexpr (kLnProducer) {
       // Row statistics of the new residual stream over THIS WARP'S 128 columns (GEMM_LN_PART), about a pivot (the first element of
       // the row in the warp's first chunk, broadcast inside the 8 lanes that share a row) so that a large common offset of the
