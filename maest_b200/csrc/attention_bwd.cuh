@@ -256,12 +256,17 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
         // only the clip's last key tile and last query tile have rows / keys to mask: everywhere else the per-element
         // compare + select pairs (30 % of this kernel's instructions, r02c_prof_attention_bwd) are skipped
         if (full_tile) {
+          // packed fp32x2: per PAIR of scores one FFMA2 (exponent), two MUFU, one FFMA2 (dP * scale - delta * scale), one FMUL2
+          // and the two packs -- 3.5 issue slots per element instead of ~7
+          const u64 sc2 = f2_packf(sc, sc), nlse2 = f2_packf(-lse2, -lse2);
+          const u64 scale2 = f2_packf(scale, scale), ndlt2 = f2_packf(-dlt * scale, -dlt * scale);
 #pragma unroll
           for (int k = 0; k < 32; k += 2) {
-            const float p0 = ex2_approx(fmaf(__uint_as_float(sv[k]), sc, -lse2));
-            const float p1 = ex2_approx(fmaf(__uint_as_float(sv[k + 1]), sc, -lse2));
-            const float d0 = p0 * (__uint_as_float(dv[k]) - dlt) * scale;
-            const float d1 = p1 * (__uint_as_float(dv[k + 1]) - dlt) * scale;
+            float a0, a1, d0, d1;
+            f2_unpack(f2_fma(f2_pack(sv[k], sv[k + 1]), sc2, nlse2), a0, a1);
+            const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+            const u64 t = f2_fma(f2_pack(dv[k], dv[k + 1]), scale2, ndlt2);
+            f2_unpack(f2_mul(f2_packf(p0, p1), t), d0, d1);
             pkP[k >> 1] = O16::pack(p0, p1);
             pkD[k >> 1] = O16::pack(d0, d1);
           }
