@@ -383,6 +383,7 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   if (epilogue == MAEST_EPI_RESID32 && rows_per_group > 0) return fail(-1, "gemm: RESID32 does not support row remapping");
   if ((epilogue == MAEST_EPI_STORE16 || epilogue == MAEST_EPI_GELU16) && rows_per_group > 0) return fail(-1, "gemm: the 16-bit epilogues do not support row remapping");
   if (epilogue == MAEST_EPI_GELUBWD16 && !aux16) return fail(-1, "gemm: GELUBWD16 needs the saved pre-activation (aux16)");
+  if (epilogue == MAEST_EPI_GELUBWD16 && bias) return fail(-1, "gemm: GELUBWD16 (an input gradient) takes no bias");
   if ((epilogue == MAEST_EPI_STORE16 || epilogue == MAEST_EPI_GELU16 || epilogue == MAEST_EPI_GELUBWD16) &&
       (r = make_tmap(&t_tmap_c, out, op_dtype, M, N, ld_out, 32))) return r;     // TMA-store epilogue: [32 rows x 64 columns] boxes
   if (epilogue == MAEST_EPI_GELU16 && aux16 && (r = make_tmap(&t_tmap_c2, aux16, op_dtype, M, N, ld_out, 32))) return r;

@@ -35,7 +35,7 @@ template <> struct Op16<DT_BF16> {
     return *reinterpret_cast<uint32_t*>(&h);
   }
   static __device__ __forceinline__ float2 unpack(uint32_t u) {
-    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+    return make_float2(__uint_as_float(u << 16), __uint_as_float(u & 0xffff0000u));   // (two ALU ops; the intrinsic costs PRMT + 2 shifts)
   }
   static __device__ __forceinline__ float to_f(T v) { return __bfloat162float(v); }
   static __device__ __forceinline__ T from_f(float v) { return __float2bfloat16_rn(v); }

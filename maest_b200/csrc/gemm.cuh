@@ -151,10 +151,19 @@ __device__ __forceinline__ void gelu_erf_grad_fast2(float x0, float x1, float& g
   f2_unpack(z, z0, z1);
   const float t0 = ex2_approx_ftz(q0), t1 = ex2_approx_ftz(q1);
   const float e0 = ex2_approx_ftz(z0), e1 = ex2_approx_ftz(z1);
-  float u0, u1;
-  f2_unpack(f2_sub(f2_packf(1.0f, 1.0f), f2_packf(t0, t1)), u0, u1);
+  // Phi(x) = 0.5 + copysign(0.5 - t, x) with t = Phi(-|x|) <= 0.5: one LOP3 per element instead of a compare and a select
+  float h0, h1;
+  f2_unpack(f2_sub(f2_packf(0.5f, 0.5f), f2_packf(t0, t1)), h0, h1);
+  h0 = __uint_as_float(__float_as_uint(h0) | (__float_as_uint(x0) & 0x80000000u));
+  h1 = __uint_as_float(__float_as_uint(h1) | (__float_as_uint(x1) & 0x80000000u));
   const u64 w = f2_mul(x, f2_packf(0.3989422804014327f, 0.3989422804014327f));
-  f2_unpack(f2_fma(w, f2_packf(e0, e1), f2_packf(x0 >= 0.f ? u0 : t0, x1 >= 0.f ? u1 : t1)), g0, g1);
+  f2_unpack(f2_add(f2_fma(w, f2_packf(e0, e1), f2_packf(h0, h1)), f2_packf(0.5f, 0.5f)), g0, g1);
+}
+
+// 32 contiguous, 32-byte aligned bytes of read-once global data (sm_100: LDG.E.256), not allocated in L1
+__device__ __forceinline__ void ldg256_stream(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
 }
 
 // The staging tile is addressed in the shared window explicitly: through the generic pointer ptxas emitted generic LD.E / ST.E
@@ -254,6 +263,22 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
     }
   }
   if constexpr (EPI != EPI_GELUBWD16) load_resid(0);      // (GELUBWD16 fetches its pre-activation rows in the TMEM-load layout, below)
+#ifdef GEMM_PRE_ALL
+  uint4 u_all[EPI == EPI_GELUBWD16 ? 16 : 1];
+  if constexpr (EPI == EPI_GELUBWD16) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+      const int n = n0 + cc * 32;
+      const bool ok = (m0 + lane < p.M) && (n + 32 <= p.N);
+      const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const typename O::T*>(p.aux16) + long(m0 + lane) * p.ld_out + n);
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        if (ok) ldg256_stream(src + 2 * h, u_all[4 * cc + 2 * h], u_all[4 * cc + 2 * h + 1]);
+        else u_all[4 * cc + 2 * h] = u_all[4 * cc + 2 * h + 1] = make_uint4(0u, 0u, 0u, 0u);
+      }
+    }
+  }
+#endif
   const uint32_t stg_s = smem_u32(stg);
   // bias of the next chunk is fetched while the current one is processed (its L2 / L1 latency sat on the first FADD of every chunk)
   float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -283,7 +308,19 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
         const bool ok = (m0 + lane < p.M) && (n + 32 <= p.N);
         const uint4* src = reinterpret_cast<const uint4*>(reinterpret_cast<const typename O::T*>(p.aux16) + long(m0 + lane) * p.ld_out + n);
 #pragma unroll
+#ifdef GEMM_DIAG_NOPRE
+        for (int q4 = 0; q4 < 4; ++q4) u[q4] = make_uint4(uint32_t(n), 0u, uint32_t(cc), 0u);
+#elif defined(GEMM_PRE_LDG128)
         for (int q4 = 0; q4 < 4; ++q4) u[q4] = ok ? src[q4] : make_uint4(0u, 0u, 0u, 0u);
+#else
+        // lane = row, so a warp-wide load touches 32 different rows: with 16-byte loads every request used half of each 32-byte
+        // sector and relied on L1 (a few KB beside 224 KB of shared memory) for the other half -- measured 0.15 ms of a 0.38 ms
+        // GEMM.  One 256-bit load per lane = one whole sector per lane, streamed past L1.
+        for (int h = 0; h < 2; ++h) {
+          if (ok) ldg256_stream(src + 2 * h, u[2 * h], u[2 * h + 1]);
+          else u[2 * h] = u[2 * h + 1] = make_uint4(0u, 0u, 0u, 0u);
+        }
+#endif
       }
     };
     auto release_after_last_load = [&]() {
@@ -291,7 +328,7 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
       __syncwarp();
       if (lane == 0) release_tmem();   // one arrival per warp: 8 (16 for a CTA pair, half of them remote) instead of 256 (512)
     };
-    auto process = [&](uint32_t (&v)[32], uint4 (&u)[EPI == EPI_GELUBWD16 ? 4 : 1], const int cc) {
+    auto process = [&](uint32_t (&v)[32], const uint4* u, const int cc) {
       const int n = n0 + cc * 32;
 
       // lane = row: bias / fold vectors are warp-uniform (broadcast) loads; results are packed to 16 bits, written to a
@@ -302,13 +339,15 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j));
+        if constexpr (EPI != EPI_GELUBWD16) {     // (an input gradient has no bias term)
+          if (p.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j));
+        }
         float4 a = make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]), __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
         if constexpr (kLnConsumer) {   // finish the LayerNorm: rstd * acc - rstd * mean * (W gamma) + (W beta + b)
           const float4 gg = __ldg(reinterpret_cast<const float4*>(p.ln_vec + n + 4 * j));
           a.x = fmaf(a.x, lane_r, fmaf(lane_mr, gg.x, bb.x)); a.y = fmaf(a.y, lane_r, fmaf(lane_mr, gg.y, bb.y));
           a.z = fmaf(a.z, lane_r, fmaf(lane_mr, gg.z, bb.z)); a.w = fmaf(a.w, lane_r, fmaf(lane_mr, gg.w, bb.w));
-        } else {
+        } else if constexpr (EPI != EPI_GELUBWD16) {
           a.x += bb.x; a.y += bb.y; a.z += bb.z; a.w += bb.w;
         }
         if constexpr (EPI == EPI_GELU16_SAVE) { pre16[2 * j] = O::pack(a.x, a.y); pre16[2 * j + 1] = O::pack(a.z, a.w); }
@@ -320,8 +359,12 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
           const uint32_t w0 = (j & 1) ? u[j >> 1].z : u[j >> 1].x, w1 = (j & 1) ? u[j >> 1].w : u[j >> 1].y;
           const float2 u01 = O::unpack(w0), u23 = O::unpack(w1);
           float g0, g1, g2, g3;
+#ifdef GEMM_DIAG_NOGRAD
+          g0 = u01.x; g1 = u01.y; g2 = u23.x; g3 = u23.y;
+#else
           gelu_erf_grad_fast2(u01.x, u01.y, g0, g1);
           gelu_erf_grad_fast2(u23.x, u23.y, g2, g3);
+#endif
           a.x *= g0; a.y *= g1; a.z *= g2; a.w *= g3;
           cs[4 * j] = a.x; cs[4 * j + 1] = a.y; cs[4 * j + 2] = a.z; cs[4 * j + 3] = a.w;
         }
@@ -333,7 +376,11 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
         // 16, 8, .. 1 every lane keeps the half of its values whose column bit matches its lane bit and receives the partner's
         // sums for that half: 31 shuffles + 31 adds, after which lane L holds the 32-row sum of column n + L.  Rows beyond M
         // contribute exact zeros (their accumulator rows are zero).
+#ifdef GEMM_DIAG_NOCS
+        if (false) {
+#else
         if (p.addend != nullptr) {
+#endif
 #pragma unroll
           for (int w = 16; w >= 1; w >>= 1) {
             const bool up = (lane & w) != 0;
@@ -422,6 +469,21 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
         }
       }
     };
+#ifdef GEMM_PRE_ALL
+    if constexpr (EPI == EPI_GELUBWD16) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        if (cc < nchunks) {
+          tmem_ld32(taddr + uint32_t(cc * 32), va);
+          tc_wait_ld();
+          reg_fence32(va);
+          if (cc == nchunks - 1) release_after_last_load();
+          process(va, &u_all[4 * cc], cc);
+        }
+      }
+      return;
+    }
+#endif
     if (nchunks > 0) { tmem_ld32(taddr, va); load_pre(ua, 0); }
 #pragma unroll 1
     for (int cc = 0; cc < nchunks; cc += 2) {
