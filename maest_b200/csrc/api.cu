@@ -73,6 +73,7 @@ thread_local TmapSlot g_tmap_cache[TMAP_CACHE_SLOTS];
 uint64_t g_tmap_hits = 0, g_tmap_misses = 0;
 
 int make_tmap_uncached(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+int make_tmap_f32(CUtensorMap* m, const void* ptr, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 int make_tmap(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
   const TmapKey key{ptr, rows, cols, ld, box_rows, dt};
@@ -85,7 +86,7 @@ int make_tmap(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t c
     ++g_tmap_hits;
     return 0;
   }
-  const int r = make_tmap_uncached(m, ptr, dt, rows, cols, ld, box_rows);
+  const int r = dt == MAEST_F32 ? make_tmap_f32(m, ptr, rows, cols, ld, box_rows) : make_tmap_uncached(m, ptr, dt, rows, cols, ld, box_rows);
   if (r == 0) { slot.key = key; slot.map = *m; slot.valid = true; ++g_tmap_misses; }
   return r;
 }
@@ -375,7 +376,7 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   if ((r = b_mn ? make_tmap(&tb, b, op_dtype, K, N, ldb, 64) : make_tmap(&tb, b, op_dtype, N, K, ldb, pair_kernel ? 128 : GEMM_BN))) return r;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = addend; p.ld_out = int(ld_out);
-  p.aux16 = aux16; p.k_splits = k_splits;
+  p.aux16 = aux16; p.k_splits = k_splits; p.reduce_out = 0;
   p.ln_stats = nullptr; p.ln_vec = nullptr; p.out16b = nullptr; p.ln_rows = 0;
   if (rows_per_group <= 0) { p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0; }
   else { p.rows_per_group = rows_per_group; p.group_stride = group_stride; p.row_offset = row_offset; }
@@ -387,6 +388,13 @@ int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int6
   if ((epilogue == MAEST_EPI_STORE16 || epilogue == MAEST_EPI_GELU16 || epilogue == MAEST_EPI_GELUBWD16) &&
       (r = make_tmap(&t_tmap_c, out, op_dtype, M, N, ld_out, 32))) return r;     // TMA-store epilogue: [32 rows x 64 columns] boxes
   if (epilogue == MAEST_EPI_GELU16 && aux16 && (r = make_tmap(&t_tmap_c2, aux16, op_dtype, M, N, ld_out, 32))) return r;
+  // in-place residual update (x += A W^T + b, the inference encoder's proj and fc2): the add is done by a TMA reduce into out
+  static const bool reduce_enabled = [] { const char* e = getenv("MAEST_RESID_REDUCE"); return !(e && e[0] == '0'); }();   // A/B switch
+  if (epilogue == MAEST_EPI_RESID32 && reduce_enabled && resid == reinterpret_cast<const float*>(out) && (ld_out % 4) == 0 &&
+      (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+    if ((r = make_tmap(&t_tmap_c, out, MAEST_F32, M, N, ld_out, 32))) return r;
+    p.reduce_out = 1;
+  }
   cudaStream_t st = (cudaStream_t)stream;
   return op_dtype == MAEST_BF16 ? launch_gemm_dt<DT_BF16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st)
                                 : launch_gemm_dt<DT_F16>(epilogue, a_mn != 0, b_mn != 0, ta, tb, p, st);
@@ -439,7 +447,7 @@ int32_t maest_linear_ln_fwd(const void* a, int64_t lda, const void* w, int64_t l
   if ((r = make_tmap(&tb, w, op_dtype, N, K, ldw, pair_kernel ? 128 : GEMM_BN))) return r;
   GemmParams p;
   p.M = M; p.N = N; p.K = K; p.bias = bias; p.out = out; p.resid = resid; p.addend = nullptr; p.ld_out = int(ld_out);
-  p.aux16 = nullptr; p.k_splits = 1; p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0;
+  p.aux16 = nullptr; p.k_splits = 1; p.reduce_out = 0; p.rows_per_group = 0x7fffffff; p.group_stride = 0; p.row_offset = 0;
   p.ln_stats = ln_stats; p.ln_vec = ln_vec; p.out16b = out16b; p.ln_rows = M;
   if ((epilogue == MAEST_EPI_STORE16_LN || epilogue == MAEST_EPI_GELU16_LN) && (r = make_tmap(&t_tmap_c, out, op_dtype, M, N, ld_out, 32))) return r;
   cudaStream_t st = (cudaStream_t)stream;

@@ -55,6 +55,8 @@ struct GemmParams {
   void* aux16;           // EPI_GELU16: optional second output, the pre-activation (saved for backward);
                          // EPI_GELUBWD16: input, the saved pre-activation.  Same shape / row stride as out.
   int ld_out;
+  int reduce_out;        // EPI_RESID32 with out == resid (x += A W^T + b in place): acc + bias leaves as a TMA reduce-add into out
+                         // (tmap_c = fp32 map of out, [32 rows x 32 floats] boxes); the residual never enters the SM
   int k_splits;          // >1: the K loop is split across CTAs (use with EPI_ATOMIC32)
   // LayerNorm folding (EPI_*_LN)
   float* ln_stats;       // producer: partials [N/32][ln_rows][4] = (pivot, sum (x - pivot), sum (x - pivot)^2, -) of every 32-column
@@ -197,6 +199,68 @@ __device__ __forceinline__ void gemm_epilogue_subtile(const GemmParams& p, const
   // EPI_STORE32 is the only epilogue with an output-row remap (patch tokens -> packed token buffer).  The remap needs an
   // integer division per row, so it is done ONCE per sub-tile (doing it per 32-column chunk made the patch-embed GEMM epilogue
   // 3x slower than its HBM bound); every other epilogue keeps the cheap r = m form and no extra live registers.
+  if constexpr (EPI == EPI_RESID32) {
+    if (p.reduce_out) {
+      // In-place residual update.  The load-add-store form below is bound by the latency of its own residual loads (8 warps x
+      // two 4 KB chunks in flight per SM ~ 43 GB/s per SM, just the SM's share of HBM, and nothing left for the stores): proj ran
+      // at 0.20 ms against an HBM bound of 0.10 ms.  Here the add happens in L2: every warp stages acc + bias as a
+      // [32 rows x 128 B] SWIZZLE_128B tile and fires cp.reduce.async.bulk.tensor (.add.f32); exactly one add per element, so the
+      // result is deterministic (and differs from the other form by the order of the two additions only).
+      const uint32_t stg_r = smem_u32(stg);
+      mbar_wait(tfull, aphase);
+      tc_fence_after();
+      if (nchunks == 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release_tmem();
+        return;
+      }
+      uint32_t va[32], vb[32];
+      auto emit = [&](uint32_t (&v)[32], const int cc) {
+        const int n = n0 + cc * 32;
+        if (lane == 0) tma_store_wait_read<0>();      // staging tile free again (the previous reduce has read it)
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (p.bias != nullptr) bb = __ldg(reinterpret_cast<const float4*>(p.bias + n + 4 * j));   // warp-uniform (lane = row)
+          sts_v4(stg_r + lane * 128 + ((uint32_t(j) ^ uint32_t(lane & 7)) << 4), __float_as_uint(__uint_as_float(v[4 * j]) + bb.x),
+                 __float_as_uint(__uint_as_float(v[4 * j + 1]) + bb.y), __float_as_uint(__uint_as_float(v[4 * j + 2]) + bb.z),
+                 __float_as_uint(__uint_as_float(v[4 * j + 3]) + bb.w));
+        }
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+          tma_reduce_add_2d(tmap_c, stg, n, m0);      // rows beyond M / columns beyond N are clipped by the tensor map
+          tma_store_commit();
+        }
+      };
+      auto release_after_last = [&]() {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) release_tmem();
+      };
+      tmem_ld32(taddr, va);
+#pragma unroll 1
+      for (int cc = 0; cc < nchunks; cc += 2) {
+        tc_wait_ld();
+        reg_fence32(va);
+        const bool has_b = cc + 1 < nchunks;
+        if (has_b) tmem_ld32(taddr + uint32_t((cc + 1) * 32), vb);
+        else release_after_last();
+        emit(va, cc);
+        if (has_b) {
+          tc_wait_ld();
+          reg_fence32(vb);
+          const bool has_a = cc + 2 < nchunks;
+          if (has_a) tmem_ld32(taddr + uint32_t((cc + 2) * 32), va);
+          else release_after_last();
+          emit(vb, cc + 1);
+        }
+      }
+      return;
+    }
+  }
   constexpr bool kRemap = (EPI == EPI_STORE32);
   long orow_[kRemap ? 8 : 1];
   int prow_[kRemap ? 8 : 1];

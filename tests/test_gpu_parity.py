@@ -92,8 +92,15 @@ def test_linear_epilogues_vs_fp64(dt, shape):
     assert rel(ops.linear(A, W, bias, _lib.EPI_GELU16), torch.nn.functional.gelu(ref)) < tol16
     x0 = torch.randn(M, N, generator=g).cuda()
     out = x0.clone()
-    ops.linear(A, W, bias, _lib.EPI_RESID32, resid=out, out=out)
+    ops.linear(A, W, bias, _lib.EPI_RESID32, resid=out, out=out)          # in place: the add is a TMA reduce into out
     assert rel(out, x0.double() + ref) < 1e-5
+    out2 = torch.empty_like(x0)
+    ops.linear(A, W, bias, _lib.EPI_RESID32, resid=x0, out=out2)           # out of place: load-add-store epilogue
+    assert rel(out2, x0.double() + ref) < 1e-5
+    assert float((out2 - out).abs().max()) <= 4e-6 * float(out.abs().max())     # the two forms differ by the order of two additions
+    again = x0.clone()
+    ops.linear(A, W, bias, _lib.EPI_RESID32, resid=again, out=again)
+    assert torch.equal(again, out)                                          # one add per element: deterministic
 
 
 def test_linear_identity_is_bit_exact():
