@@ -730,7 +730,9 @@ int32_t maest_attention_bwd(const void* qkv, const void* o, const void* d_o, con
   p.B = B; p.N = N; p.H = H; p.lse = lse; p.delta = delta; p.dq32 = dq32; p.dqkv16 = dqkv;
   p.scale = 0.125f; p.scale_log2 = 0.125f * 1.4426950408889634f;
   const long nd = M * H;
-  dim3 grid((N + 127) / 128, H, B);
+  const long n_items = long((N + 127) / 128) * H * B;          // persistent: one CTA per SM walks the (clip, head, key tile) items
+  const int sms = g_num_sms[cur_device()];
+  const unsigned grid = unsigned(n_items < sms ? n_items : sms);
   const int cast_blocks = int((M + 7) / 8);
   if (op_dtype == MAEST_BF16) {
     attn_delta_kernel<DT_BF16><<<unsigned((nd + 255) / 256), 256, 0, st>>>(o, d_o, delta, B, N, H);

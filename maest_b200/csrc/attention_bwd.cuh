@@ -15,6 +15,11 @@
 // of MMA issue; the kernel ran at 7300 cycles per pair.
 // dQ tiles are reduced across key tiles by the TMA engine (cp.reduce.async.bulk.tensor .add on fp32, staged through a
 // swizzled smem tile) into dq32; dK/dV are written once as 16-bit.
+// PERSISTENT (round 2, late): one CTA per SM walks the (clip, head, key tile) work items.  The one-item CTA spent ~11 900 of its
+// ~44 000 cycles outside the steady state (launch, barrier init, TMEM allocation, the first K / V / Q / dO round trip, the dK / dV
+// read-out with nothing else running); now K / V are double-buffered so the next item's tiles arrive during the current one, its
+// first S / dP GEMMs are issued while the compute warps drain dK / dV, and every barrier keeps its phase across items (parities
+// come from a per-CTA count of query-tile iterations).
 #pragma once
 #include "attention.cuh"
 
@@ -28,7 +33,8 @@ constexpr int ATTB_NWG = ATTB_CWARPS / 4;
 constexpr int ATTB_CPW = 4 / ATTB_NWG;               // 32-key chunks of a row per warpgroup
 static_assert(ATTB_CWARPS == 8 || ATTB_CWARPS == 16, "two or four compute warpgroups");
 constexpr int ATTB_THREADS = (ATTB_CWARPS + 3) * 32; // + TMA warp + two MMA-issuing warps
-constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 12 + 128;   // K, V, Q[2], dO[2], P (2 halves), dS (2 halves), dQ staging (2 x [128 x 32] fp32)
+constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 14 + 128;   // (K, V)[2], Q[2], dO[2], P (2 halves), dS (2 halves), dQ staging (2 x [128 x 32] fp32)
+static_assert(ATTB_SMEM_BYTES <= 227 * 1024, "shared memory budget");
 
 struct AttnBwdParams {
   int B, N, H;
@@ -45,40 +51,48 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
                      const __grid_constant__ CUtensorMap tmap_dq, const AttnBwdParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   using O16 = Op16<DT>;
-  uint8_t* sK = smem;
-  uint8_t* sV = smem + ATT_TILE_BYTES;
-  uint8_t* sQ = smem + 2 * ATT_TILE_BYTES;    // [2]
-  uint8_t* sdO = smem + 4 * ATT_TILE_BYTES;   // [2]
-  uint8_t* sP = smem + 6 * ATT_TILE_BYTES;    // two [128 q x 64 keys] halves
-  uint8_t* sdS = smem + 8 * ATT_TILE_BYTES;   // two halves
-  uint8_t* sdQ = smem + 10 * ATT_TILE_BYTES;  // two [128 rows x 32 fp32] SWIZZLE_128B halves (TMA reduce source)
+  uint8_t* sKV = smem;                        // [2 buffers] x (K, V)
+  uint8_t* sQ = smem + 4 * ATT_TILE_BYTES;    // [2]
+  uint8_t* sdO = smem + 6 * ATT_TILE_BYTES;   // [2]
+  uint8_t* sP = smem + 8 * ATT_TILE_BYTES;    // two [128 q x 64 keys] halves
+  uint8_t* sdS = smem + 10 * ATT_TILE_BYTES;  // two halves
+  uint8_t* sdQ = smem + 12 * ATT_TILE_BYTES;  // two [128 rows x 32 fp32] SWIZZLE_128B halves (TMA reduce source)
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + ATTB_SMEM_BYTES - 128);
-  uint64_t* kv_full = bars;          // 1
-  uint64_t* qdo_full = bars + 1;     // [2]
-  uint64_t* qdo_empty = bars + 3;    // [2]
-  uint64_t* sdp_full = bars + 5;     // S_i, dP_i in TMEM
-  uint64_t* pds_full = bars + 6;     // P_i, dS_i in smem (count 128)
-  uint64_t* mma2_done = bars + 7;    // dV/dK/dQ GEMMs of iteration i retired
-  uint64_t* sdp_free = bars + 8;     // every compute warp has S_i / dP_i in registers: the TMEM buffers may take S_{i+1} / dP_{i+1}
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* kv_full = bars;          // [2]
+  uint64_t* kv_empty = bars + 2;     // [2] every GEMM of the item that used this K / V buffer has retired (one commit per issuing warp)
+  uint64_t* qdo_full = bars + 4;     // [2]
+  uint64_t* qdo_empty = bars + 6;    // [2]
+  uint64_t* sdp_full = bars + 8;     // S_i, dP_i in TMEM
+  uint64_t* pds_full = bars + 9;     // P_i, dS_i in smem (count 128)
+  uint64_t* mma2_done = bars + 10;   // dV/dK/dQ GEMMs of iteration i retired
+  uint64_t* sdp_free = bars + 11;    // every compute warp has S_i / dP_i in registers: the TMEM buffers may take S_{i+1} / dP_{i+1}
+  uint64_t* dkv_free = bars + 12;    // every compute warp has read the item's dK / dV out of TMEM: the next item may overwrite them
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int kv0 = blockIdx.x * 128;
-  const int h = blockIdx.y, b = blockIdx.z;
-  const int row_base = b * p.N;
-  const int nq = (p.N + 127) / 128;
+  const int nq = (p.N + 127) / 128;           // query tiles = key tiles per (clip, head)
+  const int n_items = p.B * p.H * nq;
+  // item -> (clip, head, key tile): key tile fastest, so the CTAs running side by side share Q / dO of a (clip, head) in L2
+  auto item_kv0 = [&](int it) { return (it % nq) * 128; };
+  auto item_h = [&](int it) { return (it / nq) % p.H; };
+  auto item_b = [&](int it) { return it / (nq * p.H); };
 
   if (threadIdx.x == 0 && (smem_u32(smem) & 1023u) != 0) {
     printf("attention_bwd: dynamic smem base not 1024-aligned\n");
     __trap();
   }
   if (warp == ATTB_CWARPS + 1 && lane == 0) {
-    mbar_init(kv_full, 1);
-    for (int i = 0; i < 2; ++i) { mbar_init(&qdo_full[i], 1); mbar_init(&qdo_empty[i], 2); }   // one commit per issuing warp
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&kv_full[i], 1);
+      mbar_init(&kv_empty[i], 2);
+      mbar_init(&qdo_full[i], 1);
+      mbar_init(&qdo_empty[i], 2);    // one commit per issuing warp
+    }
     mbar_init(sdp_full, 1);
     mbar_init(pds_full, ATTB_CWARPS * 32);
     mbar_init(mma2_done, 2);
     mbar_init(sdp_free, ATTB_CWARPS);
+    mbar_init(dkv_free, ATTB_CWARPS);
     fence_mbar_init();
   }
   if (warp == ATTB_CWARPS) {
@@ -91,55 +105,70 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   const uint32_t tmem_base = *tmem_slot;
   const uint32_t tS = tmem_base, tdP = tmem_base + 128, tdV = tmem_base + 256, tdK = tmem_base + 320, tdQ = tmem_base + 384;
 
+  // Parities.  g counts this CTA's query-tile iterations over all of its items: Q / dO stage = g & 1 with phase (g >> 1) & 1;
+  // sdp_full, pds_full, mma2_done and sdp_free complete once per iteration (parity g & 1).  n counts its items: K / V buffer
+  // n & 1 with phase (n >> 1) & 1; dkv_free completes once per item (parity n & 1).
   if (warp == ATTB_CWARPS) {
     if (lane == 0) {
-      mbar_expect_tx(kv_full, 2 * ATT_TILE_BYTES);
-      tma_load_2d(sK, &tmap_qkv, kv_full, p.H * 64 + h * 64, row_base + kv0);
-      tma_load_2d(sV, &tmap_qkv, kv_full, 2 * p.H * 64 + h * 64, row_base + kv0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nq; ++i) {
-        mbar_wait(&qdo_empty[stage], phase ^ 1);
-        mbar_expect_tx(&qdo_full[stage], 2 * ATT_TILE_BYTES);
-        tma_load_2d(sQ + stage * ATT_TILE_BYTES, &tmap_qkv, &qdo_full[stage], h * 64, row_base + i * 128);
-        tma_load_2d(sdO + stage * ATT_TILE_BYTES, &tmap_do, &qdo_full[stage], h * 64, row_base + i * 128);
-        if (++stage == 2) { stage = 0; phase ^= 1; }
+      int g = 0, n = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+        const int kv0 = item_kv0(it), h = item_h(it), row_base = item_b(it) * p.N;
+        const int ks = n & 1;
+        mbar_wait(&kv_empty[ks], ((n >> 1) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[ks], 2 * ATT_TILE_BYTES);
+        tma_load_2d(sKV + (2 * ks) * ATT_TILE_BYTES, &tmap_qkv, &kv_full[ks], p.H * 64 + h * 64, row_base + kv0);
+        tma_load_2d(sKV + (2 * ks + 1) * ATT_TILE_BYTES, &tmap_qkv, &kv_full[ks], 2 * p.H * 64 + h * 64, row_base + kv0);
+        for (int i = 0; i < nq; ++i, ++g) {
+          const int stage = g & 1;
+          mbar_wait(&qdo_empty[stage], ((g >> 1) & 1) ^ 1);
+          mbar_expect_tx(&qdo_full[stage], 2 * ATT_TILE_BYTES);
+          tma_load_2d(sQ + stage * ATT_TILE_BYTES, &tmap_qkv, &qdo_full[stage], h * 64, row_base + i * 128);
+          tma_load_2d(sdO + stage * ATT_TILE_BYTES, &tmap_do, &qdo_full[stage], h * 64, row_base + i * 128);
+        }
       }
     }
   } else if (warp == ATTB_CWARPS + 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(DT, 128, 128, 0, 0);    // S, dP: A K-major, B K-major
       constexpr uint32_t idesc_t = make_idesc(DT, 128, 64, 1, 1);     // dV, dK: A = P^T / dS^T (MN-major), B MN-major
-      constexpr uint32_t idesc_q = make_idesc(DT, 128, 64, 0, 1);     // dQ: A = dS (K-major), B = K (MN-major)
-      const uint32_t aK = smem_u32(sK), aV = smem_u32(sV), aP = smem_u32(sP), aDS = smem_u32(sdS);
-      auto issue_s_dp = [&](int stage) {
+      const uint32_t aP = smem_u32(sP);
+      // S and dP of iteration g (Q / dO stage g & 1) against the K / V buffer of item n
+      auto issue_s_dp = [&](int g, int n) {
+        const int stage = g & 1, ks = n & 1;
         const uint64_t qd = make_sdesc(smem_u32(sQ + stage * ATT_TILE_BYTES), 16, 1024);
         const uint64_t od = make_sdesc(smem_u32(sdO + stage * ATT_TILE_BYTES), 16, 1024);
-        const uint64_t kd = make_sdesc(aK, 16, 1024), vd = make_sdesc(aV, 16, 1024);
+        const uint64_t kd = make_sdesc(smem_u32(sKV + (2 * ks) * ATT_TILE_BYTES), 16, 1024);
+        const uint64_t vd = make_sdesc(smem_u32(sKV + (2 * ks + 1) * ATT_TILE_BYTES), 16, 1024);
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_ss(tS, qd + uint64_t(2 * k), kd + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
 #pragma unroll
         for (int k = 0; k < 4; ++k) mma_ss(tdP, od + uint64_t(2 * k), vd + uint64_t(2 * k), idesc_s, k ? 1u : 0u);
         tc_commit(sdp_full);
       };
-      mbar_wait(kv_full, 0);
-      mbar_wait(&qdo_full[0], 0);
-      tc_fence_after();
-      issue_s_dp(0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nq; ++i) {
-        int nstage = stage ^ 1;
-        uint32_t nphase = stage == 1 ? phase ^ 1 : phase;
-        // S / dP of the NEXT query tile go out as soon as the compute warps have read this one's out of TMEM -- not after their
-        // whole P / dS phase (r02 clocks: the compute warps then idled 1900 of 4850 cycles per iteration waiting for the scores)
-        if (i + 1 < nq) {
-          mbar_wait(sdp_free, i & 1);
-          mbar_wait(&qdo_full[nstage], nphase);
+      const int my_items = blockIdx.x < n_items ? (n_items - 1 - int(blockIdx.x)) / int(gridDim.x) + 1 : 0;
+      const int total = my_items * nq;
+      if (total > 0) {
+        mbar_wait(&kv_full[0], 0);
+        mbar_wait(&qdo_full[0], 0);
+        tc_fence_after();
+        issue_s_dp(0, 0);
+      }
+      int n = 0, i = 0;
+      for (int g = 0; g < total; ++g) {
+        const int stage = g & 1;
+        // S / dP of the NEXT iteration go out as soon as the compute warps have read this one's out of TMEM -- not after their
+        // whole P / dS phase (r02 clocks: the compute warps then idled 1900 of 4850 cycles per iteration waiting for the scores).
+        // At an item boundary the next iteration reads the other K / V buffer, loaded while this item ran.
+        if (g + 1 < total) {
+          const int n_next = (i + 1 == nq) ? n + 1 : n;
+          mbar_wait(sdp_free, g & 1);
+          if (n_next != n) mbar_wait(&kv_full[n_next & 1], (n_next >> 1) & 1);
+          mbar_wait(&qdo_full[(g + 1) & 1], ((g + 1) >> 1) & 1);
           tc_fence_after();
-          issue_s_dp(nstage);
+          issue_s_dp(g + 1, n_next);
         }
-        mbar_wait(pds_full, i & 1);
+        mbar_wait(pds_full, g & 1);
+        if (i == 0 && n > 0) mbar_wait(dkv_free, (n - 1) & 1);   // the previous item's dV has been read out
         tc_fence_after();
         const uint32_t aO = smem_u32(sdO + stage * ATT_TILE_BYTES);
 #pragma unroll
@@ -148,8 +177,11 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
                  (i | k) ? 1u : 0u);
         tc_commit(&qdo_empty[stage]);
         tc_commit(mma2_done);
-        stage = nstage;
-        phase = nphase;
+        if (++i == nq) {
+          tc_commit(&kv_empty[n & 1]);     // (this warp's last GEMM on the item's V; S / dP of the item were issued earlier)
+          i = 0;
+          ++n;
+        }
       }
     }
   } else if (warp == ATTB_CWARPS + 2) {
@@ -158,27 +190,31 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     // dV (other warp, own accumulator) and dK / dQ (this warp, own accumulators) need no order between them.
     if (lane == 0) {
       constexpr uint32_t idesc_t = make_idesc(DT, 128, 64, 1, 1);
-      constexpr uint32_t idesc_q = make_idesc(DT, 128, 64, 0, 1);
-      const uint32_t aK = smem_u32(sK), aDS = smem_u32(sdS);
-      mbar_wait(kv_full, 0);
-      int stage = 0;
-      uint32_t phase = 0;
-      for (int i = 0; i < nq; ++i) {
-        mbar_wait(pds_full, i & 1);
-        mbar_wait(&qdo_full[stage], phase);
-        tc_fence_after();
-        const uint32_t aQ = smem_u32(sQ + stage * ATT_TILE_BYTES);
+      constexpr uint32_t idesc_q = make_idesc(DT, 128, 64, 0, 1);     // dQ: A = dS (K-major), B = K (MN-major)
+      const uint32_t aDS = smem_u32(sdS);
+      int g = 0, n = 0;
+      for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+        const uint32_t aK = smem_u32(sKV + (2 * (n & 1)) * ATT_TILE_BYTES);
+        mbar_wait(&kv_full[n & 1], (n >> 1) & 1);
+        for (int i = 0; i < nq; ++i, ++g) {
+          const int stage = g & 1;
+          mbar_wait(pds_full, g & 1);
+          mbar_wait(&qdo_full[stage], (g >> 1) & 1);
+          if (i == 0 && n > 0) mbar_wait(dkv_free, (n - 1) & 1);   // the previous item's dK has been read out
+          tc_fence_after();
+          const uint32_t aQ = smem_u32(sQ + stage * ATT_TILE_BYTES);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dK[key, d] += sum_q dS[q, key] Q[q, d]
-          mma_ss(tdK, make_sdesc(aDS + uint32_t(k * 2048), 16384, 1024), make_sdesc(aQ + uint32_t(k * 2048), 8192, 1024), idesc_t,
-                 (i | k) ? 1u : 0u);
+          for (int k = 0; k < 8; ++k)   // dK[key, d] += sum_q dS[q, key] Q[q, d]
+            mma_ss(tdK, make_sdesc(aDS + uint32_t(k * 2048), 16384, 1024), make_sdesc(aQ + uint32_t(k * 2048), 8192, 1024), idesc_t,
+                   (i | k) ? 1u : 0u);
 #pragma unroll
-        for (int k = 0; k < 8; ++k)   // dQ[q, d] = sum_key dS[q, key] K[key, d]
-          mma_ss(tdQ, make_sdesc(aDS + uint32_t((k >> 2) * ATT_TILE_BYTES), 16, 1024) + uint64_t(2 * (k & 3)),
-                 make_sdesc(aK + uint32_t(k * 2048), 8192, 1024), idesc_q, k ? 1u : 0u);
-        tc_commit(&qdo_empty[stage]);
-        tc_commit(mma2_done);
-        if (++stage == 2) { stage = 0; phase ^= 1; }
+          for (int k = 0; k < 8; ++k)   // dQ[q, d] = sum_key dS[q, key] K[key, d]
+            mma_ss(tdQ, make_sdesc(aDS + uint32_t((k >> 2) * ATT_TILE_BYTES), 16, 1024) + uint64_t(2 * (k & 3)),
+                   make_sdesc(aK + uint32_t(k * 2048), 8192, 1024), idesc_q, k ? 1u : 0u);
+          tc_commit(&qdo_empty[stage]);
+          tc_commit(mma2_done);
+        }
+        tc_commit(&kv_empty[n & 1]);
       }
     }
   } else {
@@ -186,11 +222,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const float sc = p.scale_log2, scale = p.scale;
-    const long stat_base = (long(b) * p.H + h) * p.N;
     auto compute_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(ATTB_CWARPS * 32) : "memory"); };
     // dQ_i: TMEM -> swizzled smem -> global fp32 reduce-add by the TMA engine.  Rows of the tile that lie beyond this
     // clip carry dS = 0, hence dQ = 0, so adding them to the next clip's rows is harmless; rows beyond the tensor are clipped.
-    auto drain_dq = [&](int i) {
+    auto drain_dq = [&](int h, int grow) {
       if (threadIdx.x == 0) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tile
       compute_bar();
       if constexpr (ATTB_NWG == 2) {
@@ -216,116 +251,28 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
       compute_bar();
 #ifndef ATTB_DIAG_NO_REDUCE     // timing diagnostic: dQ is not accumulated (results wrong)
       if (threadIdx.x == 0) {
-        tma_reduce_add_2d(&tmap_dq, sdQ, h * 64, row_base + i * 128);
-        tma_reduce_add_2d(&tmap_dq, sdQ + ATT_TILE_BYTES, h * 64 + 32, row_base + i * 128);
+        tma_reduce_add_2d(&tmap_dq, sdQ, h * 64, grow);
+        tma_reduce_add_2d(&tmap_dq, sdQ + ATT_TILE_BYTES, h * 64 + 32, grow);
         tma_store_commit();
       }
 #endif
     };
-#ifdef ATTB_DIAG
-    unsigned dg_wait_s = 0, dg_math = 0, dg_wait_mma = 0, dg_drain = 0, dg_store = 0, dg_arrive = 0;
-    const long long dg_start = clock64();
-#define DG(var) do { const unsigned n__ = (unsigned)clock(); var += n__ - dg_t; dg_t = n__; } while (0)
-#else
-#define DG(var) do { } while (0)
-#endif
-    for (int i = 0; i < nq; ++i) {
-#ifdef ATTB_DIAG
-      unsigned dg_t = (unsigned)clock();
-#endif
-      const int qrow = i * 128 + row;
-      const bool q_ok = qrow < p.N;
-      const float lse2 = q_ok ? p.lse[stat_base + qrow] : 0.f;
-      const float dlt = q_ok ? p.delta[stat_base + qrow] : 0.f;
-      const bool full_tile = (kv0 + 128 <= p.N) && (i * 128 + 128 <= p.N);     // CTA-uniform
-      mbar_wait(sdp_full, i & 1);
-      tc_fence_after();
-      DG(dg_wait_s);
-#pragma unroll 1
-      for (int c = ATTB_CPW * wg; c < ATTB_CPW * wg + ATTB_CPW; ++c) {
-        uint32_t sv[32], dv[32];
-        tmem_ld32(tS + lane_off + uint32_t(c * 32), sv);
-        tmem_ld32(tdP + lane_off + uint32_t(c * 32), dv);
-        tc_wait_ld();
-        if (c == ATTB_CPW * wg + ATTB_CPW - 1) {       // this warp's last chunk of S_i / dP_i is in registers
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(sdp_free);
-        }
-        uint32_t pkP[16], pkD[16];
-        // only the clip's last key tile and last query tile have rows / keys to mask: everywhere else the per-element
-        // compare + select pairs (30 % of this kernel's instructions, r02c_prof_attention_bwd) are skipped
-        if (full_tile) {
-          // packed fp32x2: per PAIR of scores one FFMA2 (exponent), two MUFU, one FFMA2 (dP * scale - delta * scale), one FMUL2
-          // and the two packs -- 3.5 issue slots per element instead of ~7
-          const u64 sc2 = f2_packf(sc, sc), nlse2 = f2_packf(-lse2, -lse2);
-          const u64 scale2 = f2_packf(scale, scale), ndlt2 = f2_packf(-dlt * scale, -dlt * scale);
-#pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            float a0, a1, d0, d1;
-            f2_unpack(f2_fma(f2_pack(sv[k], sv[k + 1]), sc2, nlse2), a0, a1);
-            const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
-            const u64 t = f2_fma(f2_pack(dv[k], dv[k + 1]), scale2, ndlt2);
-            f2_unpack(f2_mul(f2_packf(p0, p1), t), d0, d1);
-            pkP[k >> 1] = O16::pack(p0, p1);
-            pkD[k >> 1] = O16::pack(d0, d1);
-          }
-        } else {
-#pragma unroll
-          for (int k = 0; k < 32; k += 2) {
-            const int key = kv0 + c * 32 + k;
-            float p0 = ex2_approx(fmaf(__uint_as_float(sv[k]), sc, -lse2));
-            float p1 = ex2_approx(fmaf(__uint_as_float(sv[k + 1]), sc, -lse2));
-            if (!q_ok || key >= p.N) p0 = 0.f;
-            if (!q_ok || key + 1 >= p.N) p1 = 0.f;
-            const float d0 = p0 * (__uint_as_float(dv[k]) - dlt) * scale;
-            const float d1 = p1 * (__uint_as_float(dv[k + 1]) - dlt) * scale;
-            pkP[k >> 1] = O16::pack(p0, p1);
-            pkD[k >> 1] = O16::pack(d0, d1);
-          }
-        }
-        DG(dg_math);
-        if (c == ATTB_CPW * wg && i > 0) {   // the previous iteration's GEMMs must retire before P/dS smem is overwritten
-          mbar_wait(mma2_done, (i - 1) & 1);
-          tc_fence_after();
-          DG(dg_wait_mma);
-          drain_dq(i - 1);
-          DG(dg_drain);
-        }
-        uint8_t* bp = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
-        uint8_t* bd = sdS + (c >> 1) * ATT_TILE_BYTES + row * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4) {
-          const int chunk = (((c & 1) * 4 + q4) ^ (row & 7)) * 16;
-          *reinterpret_cast<uint4*>(bp + chunk) = make_uint4(pkP[4 * q4], pkP[4 * q4 + 1], pkP[4 * q4 + 2], pkP[4 * q4 + 3]);
-          *reinterpret_cast<uint4*>(bd + chunk) = make_uint4(pkD[4 * q4], pkD[4 * q4 + 1], pkD[4 * q4 + 2], pkD[4 * q4 + 3]);
-        }
-        DG(dg_store);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      mbar_arrive(pds_full);
-      DG(dg_arrive);
-    }
-#ifdef ATTB_DIAG
-    if (blockIdx.x == 1 && blockIdx.y == 0 && blockIdx.z == 0 && (threadIdx.x == 0 || threadIdx.x == 128))
-      printf("ATTB_DIAG wg %d nq %d per-iteration cycles: wait_s %u math %u wait_mma2 %u drain %u store %u fence+arrive %u | loop total %lld\n", wg, nq,
-             dg_wait_s / nq, dg_math / nq, dg_wait_mma / nq, dg_drain / nq, dg_store / nq, dg_arrive / nq, (clock64() - dg_start) / nq);
-#endif
-    mbar_wait(mma2_done, (nq - 1) & 1);
-    tc_fence_after();
-    drain_dq(nq - 1);
-    // dK_j, dV_j -> 16-bit column blocks of dqkv
-    const int key = kv0 + row;
-    typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.dqkv16) + long(row_base + key) * (3 * p.H * 64) + h * 64;
-    {
-      // two warpgroups: one takes dK, the other dV; four: (dK | dV) x (columns 0-31 | 32-63)
+    // dK_j, dV_j of a finished item -> 16-bit column blocks of dqkv; two warpgroups: one takes dK, the other dV; four:
+    // (dK | dV) x (columns 0-31 | 32-63)
+    auto drain_dkv = [&](int kv0, int h, int row_base) {
+      const int key = kv0 + row;
+      typename O16::T* dst = reinterpret_cast<typename O16::T*>(p.dqkv16) + long(row_base + key) * (3 * p.H * 64) + h * 64;
       const int which = ATTB_NWG == 2 ? wg : (wg >> 1);     // 0: dK -> column block 1, 1: dV -> column block 2
 #pragma unroll 1
       for (int c = (ATTB_NWG == 2 ? 0 : (wg & 1)); c < (ATTB_NWG == 2 ? 2 : (wg & 1) + 1); ++c) {
         uint32_t v[32];
         tmem_ld32((which ? tdV : tdK) + lane_off + uint32_t(c * 32), v);
         tc_wait_ld();
+        if (c == (ATTB_NWG == 2 ? 1 : (wg & 1))) {      // this warp's last read of the item's dK / dV accumulators
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(dkv_free);
+        }
         if (key < p.N) {
           typename O16::T* d = dst + (which + 1) * p.H * 64 + c * 32;
 #pragma unroll
@@ -336,7 +283,134 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
                          O16::pack(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
         }
       }
+    };
+#ifdef ATTB_DIAG
+    unsigned dg_wait_s = 0, dg_math = 0, dg_wait_mma = 0, dg_drain = 0, dg_store = 0, dg_arrive = 0, dg_item = 0;
+    const long long dg_start = clock64();
+#define DG(var) do { const unsigned n__ = (unsigned)clock(); var += n__ - dg_t; dg_t = n__; } while (0)
+#else
+#define DG(var) do { } while (0)
+#endif
+    int g = 0, n = 0;
+    int pv_kv0 = 0, pv_h = 0, pv_row = 0;          // the previous iteration's item and first query row (for the deferred read-outs)
+    // this thread's row statistics (log-sum-exp, delta) are fetched one iteration ahead: loaded at the top of the iteration that
+    // uses them, their global-load latency sat in front of the first exponential of every iteration
+    float lse_n = 0.f, dlt_n = 0.f;
+    auto fetch_stats = [&](int it, int i) {
+      const int qrow = i * 128 + row;
+      const bool ok = it < n_items && qrow < p.N;
+      const long at = (long(item_b(ok ? it : 0)) * p.H + item_h(ok ? it : 0)) * p.N + qrow;
+      lse_n = ok ? __ldg(p.lse + at) : 0.f;
+      dlt_n = ok ? __ldg(p.delta + at) : 0.f;
+    };
+    fetch_stats(blockIdx.x, 0);
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
+      const int kv0 = item_kv0(it), h = item_h(it), b = item_b(it);
+      const int row_base = b * p.N;
+      for (int i = 0; i < nq; ++i, ++g) {
+#ifdef ATTB_DIAG
+        unsigned dg_t = (unsigned)clock();
+#endif
+        const int qrow = i * 128 + row;
+        const bool q_ok = qrow < p.N;
+#ifdef ATTB_NO_STATS_PREFETCH
+        fetch_stats(it, i);
+        const float lse2 = lse_n, dlt = dlt_n;
+#else
+        const float lse2 = lse_n, dlt = dlt_n;
+        if (i + 1 < nq) fetch_stats(it, i + 1);
+        else fetch_stats(it + int(gridDim.x), 0);
+#endif
+        const bool full_tile = (kv0 + 128 <= p.N) && (i * 128 + 128 <= p.N);     // CTA-uniform
+        mbar_wait(sdp_full, g & 1);
+        tc_fence_after();
+        DG(dg_wait_s);
+#pragma unroll 1
+        for (int c = ATTB_CPW * wg; c < ATTB_CPW * wg + ATTB_CPW; ++c) {
+          uint32_t sv[32], dv[32];
+          tmem_ld32(tS + lane_off + uint32_t(c * 32), sv);
+          tmem_ld32(tdP + lane_off + uint32_t(c * 32), dv);
+          tc_wait_ld();
+          if (c == ATTB_CPW * wg + ATTB_CPW - 1) {       // this warp's last chunk of S_i / dP_i is in registers
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(sdp_free);
+          }
+          uint32_t pkP[16], pkD[16];
+          // only the clip's last key tile and last query tile have rows / keys to mask: everywhere else the per-element
+          // compare + select pairs (30 % of this kernel's instructions, r02c_prof_attention_bwd) are skipped
+          if (full_tile) {
+            // packed fp32x2: per PAIR of scores one FFMA2 (exponent), two MUFU, one FFMA2 (dP * scale - delta * scale), one FMUL2
+            // and the two packs -- 3.5 issue slots per element instead of ~7
+            const u64 sc2 = f2_packf(sc, sc), nlse2 = f2_packf(-lse2, -lse2);
+            const u64 scale2 = f2_packf(scale, scale), ndlt2 = f2_packf(-dlt * scale, -dlt * scale);
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+              float a0, a1, d0, d1;
+              f2_unpack(f2_fma(f2_pack(sv[k], sv[k + 1]), sc2, nlse2), a0, a1);
+              const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+              const u64 t = f2_fma(f2_pack(dv[k], dv[k + 1]), scale2, ndlt2);
+              f2_unpack(f2_mul(f2_packf(p0, p1), t), d0, d1);
+              pkP[k >> 1] = O16::pack(p0, p1);
+              pkD[k >> 1] = O16::pack(d0, d1);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; k += 2) {
+              const int key = kv0 + c * 32 + k;
+              float p0 = ex2_approx(fmaf(__uint_as_float(sv[k]), sc, -lse2));
+              float p1 = ex2_approx(fmaf(__uint_as_float(sv[k + 1]), sc, -lse2));
+              if (!q_ok || key >= p.N) p0 = 0.f;
+              if (!q_ok || key + 1 >= p.N) p1 = 0.f;
+              const float d0 = p0 * (__uint_as_float(dv[k]) - dlt) * scale;
+              const float d1 = p1 * (__uint_as_float(dv[k + 1]) - dlt) * scale;
+              pkP[k >> 1] = O16::pack(p0, p1);
+              pkD[k >> 1] = O16::pack(d0, d1);
+            }
+          }
+          DG(dg_math);
+          // The previous iteration's GEMMs must retire before P/dS smem is overwritten; its dQ is read out here, behind this
+          // iteration's first chunk of arithmetic (which hides the GEMMs' latency).  An item boundary is no different -- the
+          // first scores of the new item were issued during the old one -- except that the old item's dK / dV leave too.
+          if (c == ATTB_CPW * wg && g > 0) {
+            mbar_wait(mma2_done, (g - 1) & 1);
+            tc_fence_after();
+            DG(dg_wait_mma);
+            drain_dq(pv_h, pv_row);
+            DG(dg_drain);
+            if (i == 0) {
+              drain_dkv(pv_kv0, pv_h, pv_row - (nq - 1) * 128);
+              DG(dg_item);
+            }
+          }
+          uint8_t* bp = sP + (c >> 1) * ATT_TILE_BYTES + row * 128;
+          uint8_t* bd = sdS + (c >> 1) * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            const int chunk = (((c & 1) * 4 + q4) ^ (row & 7)) * 16;
+            *reinterpret_cast<uint4*>(bp + chunk) = make_uint4(pkP[4 * q4], pkP[4 * q4 + 1], pkP[4 * q4 + 2], pkP[4 * q4 + 3]);
+            *reinterpret_cast<uint4*>(bd + chunk) = make_uint4(pkD[4 * q4], pkD[4 * q4 + 1], pkD[4 * q4 + 2], pkD[4 * q4 + 3]);
+          }
+          DG(dg_store);
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(pds_full);
+        DG(dg_arrive);
+        pv_kv0 = kv0; pv_h = h; pv_row = row_base + i * 128;
+      }
     }
+    if (g > 0) {      // the CTA's last item
+      mbar_wait(mma2_done, (g - 1) & 1);
+      tc_fence_after();
+      drain_dq(pv_h, pv_row);
+      drain_dkv(pv_kv0, pv_h, pv_row - (nq - 1) * 128);
+    }
+#ifdef ATTB_DIAG
+    if (blockIdx.x == 1 && (threadIdx.x == 0 || threadIdx.x == 128) && g > 0)
+      printf("ATTB_DIAG wg %d nq %d items %d per-iteration cycles: wait_s %u math %u wait_mma2 %u drain %u store %u fence+arrive %u | per item: end %u | total per iteration %lld\n",
+             wg, nq, n, dg_wait_s / g, dg_math / g, dg_wait_mma / g, dg_drain / g, dg_store / g, dg_arrive / g, dg_item / n, (clock64() - dg_start) / g);
+#endif
   }
 
   // the last reduce-add must have finished READING its staging tile before the CTA (and its shared memory) goes away; its global

@@ -103,7 +103,7 @@ def test_backward_gemm_variants(dt):
 
 
 @pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
-@pytest.mark.parametrize("BN", [(1, 128), (2, 100), (2, 866), (1, 300)])
+@pytest.mark.parametrize("BN", [(1, 128), (2, 100), (2, 866), (1, 300), (20, 300), (5, 700)])   # (the last two: several work items per persistent CTA)
 def test_attention_backward_vs_autograd(dt, BN):
     B, N = BN
     g = torch.Generator().manual_seed(B * 100 + N)
@@ -111,7 +111,7 @@ def test_attention_backward_vs_autograd(dt, BN):
     d_o = (torch.randn(B * N, 768, generator=g) * 0.1).to(dt).cuda()
     o, lse = ops.attention(qkv, B, N, 12, 0, save_lse=True)
     qd = qkv.double().requires_grad_(True)
-    q, k, v = qd.view(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4)
+    q, k, v = qd.view(B, N, 3, 12, 64).permute(2, 0, 3, 1, 4)           # (float64 autograd on the GPU)
     s = (q @ k.transpose(-1, -2)) * 0.125
     (torch.softmax(s, -1) @ v).transpose(1, 2).reshape(B * N, 768).backward(d_o.double())
     assert float((lse.double() - torch.logsumexp(s, -1) * 1.4426950408889634).abs().max()) < 1e-4
