@@ -32,9 +32,42 @@ constexpr int ATTB_CWARPS = ATTB_COMPUTE_WARPS;      // compute warps: 8 (two wa
 constexpr int ATTB_NWG = ATTB_CWARPS / 4;
 constexpr int ATTB_CPW = 4 / ATTB_NWG;               // 32-key chunks of a row per warpgroup
 static_assert(ATTB_CWARPS == 8 || ATTB_CWARPS == 16, "two or four compute warpgroups");
-constexpr int ATTB_THREADS = (ATTB_CWARPS + 3) * 32; // + TMA warp + two MMA-issuing warps
+// + one warpgroup of TMA warp, two MMA-issuing warps and an idle warp, + one warpgroup that reads dQ_i out of TMEM and hands it to
+// the TMA reduce (that read-out was 730 of the compute warps' ~4900 cycles per iteration, and they are the critical path)
+constexpr int ATTB_THREADS = (ATTB_CWARPS + 8) * 32;
+// setmaxnreg moves registers inside the CTA's allocation AT LAUNCH (threads x the kernel's register count: 768 x 80 here), not
+// inside the whole register file: what the compute warps take must have been released by the two auxiliary warpgroups -- a
+// setmaxnreg.inc that asks for more blocks forever (bring-up: 104 / 40 hung with the compute warps parked on it).
+constexpr int ATTB_REGS_LAUNCH = ATTB_CWARPS == 16 ? 80 : 128;      // what ptxas settles on under __launch_bounds__(ATTB_THREADS, 1)
+constexpr int ATTB_REGS_COMPUTE = ATTB_CWARPS == 16 ? 104 : 168, ATTB_REGS_AUX = ATTB_CWARPS == 16 ? 32 : 48;
+static_assert(ATTB_CWARPS * 32 * (ATTB_REGS_COMPUTE - ATTB_REGS_LAUNCH) <= 256 * (ATTB_REGS_LAUNCH - ATTB_REGS_AUX), "setmaxnreg budget");
 constexpr int ATTB_SMEM_BYTES = ATT_TILE_BYTES * 14 + 128;   // (K, V)[2], Q[2], dO[2], P (2 halves), dS (2 halves), dQ staging (2 x [128 x 32] fp32)
 static_assert(ATTB_SMEM_BYTES <= 227 * 1024, "shared memory budget");
+
+// Of every 8 score pairs of a full tile, ATTB_NPOLY take their exponential on the FMA pipe (Cody-Waite + minimax cubic, relative
+// error 7.7e-5, as in the forward chains kernel): 16 compute warps x 32 exponentials are 1024 MUFU cycles per sub-partition and
+// iteration, the longest single item of the P / dS phase.
+#ifndef ATTB_NPOLY
+#define ATTB_NPOLY 0      // measured (same box, 64 x 866): 0/8 0.820 ms, 2/8 0.835 ms, 3/8 and 4/8 spill under the register cap (1.15 ms):
+                          // the phase is as much issue-bound as MUFU-bound, moving exponentials to the FMA pipe buys nothing
+#endif
+// 2^a for a packed pair, a <= 0 (clamped at -126, where the result is 1.2e-38 ~ 0)
+__device__ __forceinline__ void attb_ex2_poly2(const u64 a_in, float& p0, float& p1) {
+  float a0, a1;
+  f2_unpack(a_in, a0, a1);
+  const u64 a = f2_packf(fmaxf(a0, -126.0f), fmaxf(a1, -126.0f));
+  const u64 t = f2_add(a, f2_packf(12582912.f, 12582912.f));
+  const u64 f = f2_add(t, f2_packf(-12582912.f, -12582912.f));
+  const u64 r = f2_sub(a, f);
+  u64 q = f2_fma(r, f2_packf(0.05519810691475868f, 0.05519810691475868f), f2_packf(0.24267712235450745f, 0.24267712235450745f));
+  q = f2_fma(q, r, f2_packf(0.6932618021965027f, 0.6932618021965027f));
+  q = f2_fma(q, r, f2_packf(0.9999227523803711f, 0.9999227523803711f));
+  float q0, q1, t0, t1;
+  f2_unpack(q, q0, q1);
+  f2_unpack(t, t0, t1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
+}
 
 struct AttnBwdParams {
   int B, N, H;
@@ -67,7 +100,8 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   uint64_t* mma2_done = bars + 10;   // dV/dK/dQ GEMMs of iteration i retired
   uint64_t* sdp_free = bars + 11;    // every compute warp has S_i / dP_i in registers: the TMEM buffers may take S_{i+1} / dP_{i+1}
   uint64_t* dkv_free = bars + 12;    // every compute warp has read the item's dK / dV out of TMEM: the next item may overwrite them
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  uint64_t* dq_free = bars + 13;     // the drain warpgroup has dQ_i in registers: the accumulator may take dQ_{i+1}
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nq = (p.N + 127) / 128;           // query tiles = key tiles per (clip, head)
@@ -93,6 +127,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     mbar_init(mma2_done, 2);
     mbar_init(sdp_free, ATTB_CWARPS);
     mbar_init(dkv_free, ATTB_CWARPS);
+    mbar_init(dq_free, 4);
     fence_mbar_init();
   }
   if (warp == ATTB_CWARPS) {
@@ -108,7 +143,56 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
   // Parities.  g counts this CTA's query-tile iterations over all of its items: Q / dO stage = g & 1 with phase (g >> 1) & 1;
   // sdp_full, pds_full, mma2_done and sdp_free complete once per iteration (parity g & 1).  n counts its items: K / V buffer
   // n & 1 with phase (n >> 1) & 1; dkv_free completes once per item (parity n & 1).
-  if (warp == ATTB_CWARPS) {
+  // (each setmaxnreg sits at the top of its role's branch: ptxas budgets registers per branch only then)
+  if (warp >= ATTB_CWARPS + 4) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATTB_REGS_AUX));
+    // dQ_i: TMEM -> swizzled smem -> global fp32 reduce-add by the TMA engine.  Rows of the tile that lie beyond this
+    // clip carry dS = 0, hence dQ = 0, so adding them to the next clip's rows is harmless; rows beyond the tensor are clipped.
+    const int dw = warp & 3;                       // TMEM lane quarter (ATTB_CWARPS + 4 is a multiple of 4)
+    const int row = dw * 32 + lane;
+    const uint32_t lane_off = uint32_t(dw * 32) << 16;
+    const bool elected = (warp == ATTB_CWARPS + 4) && lane == 0;     // issues (and waits for) every bulk reduce of the CTA
+    auto drain_bar = [&]() { asm volatile("bar.sync 2, 128;" ::: "memory"); };
+    int g = 0;
+    for (int it = blockIdx.x; it < n_items; it += gridDim.x) {
+      const int h = item_h(it), row_base = item_b(it) * p.N;
+      for (int i = 0; i < nq; ++i, ++g) {
+        mbar_wait(mma2_done, g & 1);
+        tc_fence_after();
+        if (elected) tma_store_wait_read<0>();     // the previous reduce has finished reading the staging tiles
+        drain_bar();
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {              // 16 of the 64 dQ columns = half of a [128 x 32] fp32 staging tile
+          uint32_t v[16];
+          tmem_ld16(tdQ + lane_off + uint32_t(c * 16), v);
+          tc_wait_ld();
+          if (c == 3) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(dq_free);
+          }
+          uint8_t* base = sdQ + (c >> 1) * ATT_TILE_BYTES + row * 128;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4)
+            *reinterpret_cast<uint4*>(base + (((4 * (c & 1) + q4) ^ (row & 7)) << 4)) = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
+        }
+        fence_proxy_async_smem();
+        drain_bar();
+#ifndef ATTB_DIAG_NO_REDUCE     // timing diagnostic: dQ is not accumulated (results wrong)
+        if (elected) {
+          tma_reduce_add_2d(&tmap_dq, sdQ, h * 64, row_base + i * 128);
+          tma_reduce_add_2d(&tmap_dq, sdQ + ATT_TILE_BYTES, h * 64 + 32, row_base + i * 128);
+          tma_store_commit();
+        }
+#endif
+      }
+    }
+    // the last reduce-add must have finished READING its staging tile before the CTA (and its shared memory) goes away; its
+    // global writes complete on their own before the grid does (waiting for them here cost ~2 us per CTA)
+    if (elected) tma_store_wait_read<0>();
+  } else if (warp >= ATTB_CWARPS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(ATTB_REGS_AUX));
+    if (warp == ATTB_CWARPS) {
     if (lane == 0) {
       int g = 0, n = 0;
       for (int it = blockIdx.x; it < n_items; it += gridDim.x, ++n) {
@@ -127,7 +211,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
         }
       }
     }
-  } else if (warp == ATTB_CWARPS + 1) {
+    } else if (warp == ATTB_CWARPS + 1) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(DT, 128, 128, 0, 0);    // S, dP: A K-major, B K-major
       constexpr uint32_t idesc_t = make_idesc(DT, 128, 64, 1, 1);     // dV, dK: A = P^T / dS^T (MN-major), B MN-major
@@ -184,7 +268,7 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
         }
       }
     }
-  } else if (warp == ATTB_CWARPS + 2) {
+    } else if (warp == ATTB_CWARPS + 2) {
     // second issuing warp: dK and dQ (both read dS).  A single thread issues one tcgen05.mma per ~53 cycles whatever its N
     // (profiles/r02_ubench_mma_issue.txt), so the 24 N = 64 instructions of an iteration were 1270 issue cycles on one warp;
     // dV (other warp, own accumulator) and dK / dQ (this warp, own accumulators) need no order between them.
@@ -207,6 +291,10 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           for (int k = 0; k < 8; ++k)   // dK[key, d] += sum_q dS[q, key] Q[q, d]
             mma_ss(tdK, make_sdesc(aDS + uint32_t(k * 2048), 16384, 1024), make_sdesc(aQ + uint32_t(k * 2048), 8192, 1024), idesc_t,
                    (i | k) ? 1u : 0u);
+          if (g > 0) {                  // the drain warpgroup holds dQ of the previous iteration in registers
+            mbar_wait(dq_free, (g - 1) & 1);
+            tc_fence_after();
+          }
 #pragma unroll
           for (int k = 0; k < 8; ++k)   // dQ[q, d] = sum_key dS[q, key] K[key, d]
             mma_ss(tdQ, make_sdesc(aDS + uint32_t((k >> 2) * ATT_TILE_BYTES), 16, 1024) + uint64_t(2 * (k & 3)),
@@ -217,46 +305,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
         tc_commit(&kv_empty[n & 1]);
       }
     }
+    }
   } else {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(ATTB_REGS_COMPUTE));
     const int wg = warp >> 2;                      // which half of the keys / staging columns / (dK | dV) this warp owns
     const int row = (warp & 3) * 32 + lane;
     const uint32_t lane_off = uint32_t((warp & 3) * 32) << 16;
     const float sc = p.scale_log2, scale = p.scale;
-    auto compute_bar = [&]() { asm volatile("bar.sync 1, %0;" ::"n"(ATTB_CWARPS * 32) : "memory"); };
-    // dQ_i: TMEM -> swizzled smem -> global fp32 reduce-add by the TMA engine.  Rows of the tile that lie beyond this
-    // clip carry dS = 0, hence dQ = 0, so adding them to the next clip's rows is harmless; rows beyond the tensor are clipped.
-    auto drain_dq = [&](int h, int grow) {
-      if (threadIdx.x == 0) tma_store_wait_read<0>();   // previous reduce has finished reading the staging tile
-      compute_bar();
-      if constexpr (ATTB_NWG == 2) {
-        const int c = wg;
-        uint32_t v[32];
-        tmem_ld32(tdQ + lane_off + uint32_t(c * 32), v);
-        tc_wait_ld();
-        uint8_t* base = sdQ + c * ATT_TILE_BYTES + row * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 8; ++q4)
-          *reinterpret_cast<uint4*>(base + ((q4 ^ (row & 7)) << 4)) = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-      } else {      // four warpgroups: 16 of the 64 dQ columns each = half of a [128 x 32] fp32 staging tile
-        uint32_t v[16];
-        tmem_ld16(tdQ + lane_off + uint32_t(wg * 16), v);
-        tc_wait_ld();
-        uint8_t* base = sdQ + (wg >> 1) * ATT_TILE_BYTES + row * 128;
-#pragma unroll
-        for (int q4 = 0; q4 < 4; ++q4)
-          *reinterpret_cast<uint4*>(base + (((4 * (wg & 1) + q4) ^ (row & 7)) << 4)) = make_uint4(v[4 * q4], v[4 * q4 + 1], v[4 * q4 + 2], v[4 * q4 + 3]);
-      }
-      fence_proxy_async_smem();
-      tc_fence_before();
-      compute_bar();
-#ifndef ATTB_DIAG_NO_REDUCE     // timing diagnostic: dQ is not accumulated (results wrong)
-      if (threadIdx.x == 0) {
-        tma_reduce_add_2d(&tmap_dq, sdQ, h * 64, grow);
-        tma_reduce_add_2d(&tmap_dq, sdQ + ATT_TILE_BYTES, h * 64 + 32, grow);
-        tma_store_commit();
-      }
-#endif
-    };
     // dK_j, dV_j of a finished item -> 16-bit column blocks of dqkv; two warpgroups: one takes dK, the other dV; four:
     // (dK | dV) x (columns 0-31 | 32-63)
     auto drain_dkv = [&](int kv0, int h, int row_base) {
@@ -346,9 +401,15 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
             const u64 scale2 = f2_packf(scale, scale), ndlt2 = f2_packf(-dlt * scale, -dlt * scale);
 #pragma unroll
             for (int k = 0; k < 32; k += 2) {
-              float a0, a1, d0, d1;
-              f2_unpack(f2_fma(f2_pack(sv[k], sv[k + 1]), sc2, nlse2), a0, a1);
-              const float p0 = ex2_approx(a0), p1 = ex2_approx(a1);
+              float a0, a1, d0, d1, p0, p1;
+              const u64 a = f2_fma(f2_pack(sv[k], sv[k + 1]), sc2, nlse2);
+              if ((((k >> 1) * ATTB_NPOLY) & 7) < ATTB_NPOLY) {      // the polynomial pairs spread over each group of 8
+                attb_ex2_poly2(a, p0, p1);
+              } else {
+                f2_unpack(a, a0, a1);
+                p0 = ex2_approx(a0);
+                p1 = ex2_approx(a1);
+              }
               const u64 t = f2_fma(f2_pack(dv[k], dv[k + 1]), scale2, ndlt2);
               f2_unpack(f2_mul(f2_packf(p0, p1), t), d0, d1);
               pkP[k >> 1] = O16::pack(p0, p1);
@@ -369,15 +430,13 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
             }
           }
           DG(dg_math);
-          // The previous iteration's GEMMs must retire before P/dS smem is overwritten; its dQ is read out here, behind this
-          // iteration's first chunk of arithmetic (which hides the GEMMs' latency).  An item boundary is no different -- the
-          // first scores of the new item were issued during the old one -- except that the old item's dK / dV leave too.
+          // The previous iteration's GEMMs must retire before P/dS smem is overwritten (this iteration's first chunk of arithmetic
+          // hides their latency; dQ leaves through the drain warpgroup).  An item boundary is no different -- the first scores of
+          // the new item were issued during the old one -- except that the old item's dK / dV are read out here.
           if (c == ATTB_CPW * wg && g > 0) {
             mbar_wait(mma2_done, (g - 1) & 1);
             tc_fence_after();
             DG(dg_wait_mma);
-            drain_dq(pv_h, pv_row);
-            DG(dg_drain);
             if (i == 0) {
               drain_dkv(pv_kv0, pv_h, pv_row - (nq - 1) * 128);
               DG(dg_item);
@@ -403,7 +462,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
     if (g > 0) {      // the CTA's last item
       mbar_wait(mma2_done, (g - 1) & 1);
       tc_fence_after();
-      drain_dq(pv_h, pv_row);
       drain_dkv(pv_kv0, pv_h, pv_row - (nq - 1) * 128);
     }
 #ifdef ATTB_DIAG
@@ -413,9 +471,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
 #endif
   }
 
-  // the last reduce-add must have finished READING its staging tile before the CTA (and its shared memory) goes away; its global
-  // writes complete on their own before the grid does (waiting for them here cost ~2 us per CTA, after the dK / dV stores)
-  if (threadIdx.x == 0) tma_store_wait_read<0>();
   tc_fence_before();
   __syncthreads();
   if (warp == ATTB_CWARPS) {
