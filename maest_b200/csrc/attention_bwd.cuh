@@ -291,6 +291,9 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           for (int k = 0; k < 8; ++k)   // dK[key, d] += sum_q dS[q, key] Q[q, d]
             mma_ss(tdK, make_sdesc(aDS + uint32_t(k * 2048), 16384, 1024), make_sdesc(aQ + uint32_t(k * 2048), 8192, 1024), idesc_t,
                    (i | k) ? 1u : 0u);
+          // Q_i is not read again: the stage goes back to the TMA warp before the dQ GEMMs (and before the wait for the dQ
+          // accumulator) -- its refill is a 2000-cycle round trip that the S / dP issue two iterations on waits for
+          tc_commit(&qdo_empty[stage]);
           if (g > 0) {                  // the drain warpgroup holds dQ of the previous iteration in registers
             mbar_wait(dq_free, (g - 1) & 1);
             tc_fence_after();
@@ -299,7 +302,6 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           for (int k = 0; k < 8; ++k)   // dQ[q, d] = sum_key dS[q, key] K[key, d]
             mma_ss(tdQ, make_sdesc(aDS + uint32_t((k >> 2) * ATT_TILE_BYTES), 16, 1024) + uint64_t(2 * (k & 3)),
                    make_sdesc(aK + uint32_t(k * 2048), 8192, 1024), idesc_q, k ? 1u : 0u);
-          tc_commit(&qdo_empty[stage]);
           tc_commit(mma2_done);
         }
         tc_commit(&kv_empty[n & 1]);
