@@ -155,6 +155,10 @@ int32_t maest_layernorm_fwd(const float* x, const float* w, const float* b, void
  * (m / rows_per_group) * group_stride + row_offset + m % rows_per_group  (rows_per_group = 0 -> identity).
  * addend: optional fp32 [rows_per_group, N] table added in MAEST_EPI_STORE32; for MAEST_EPI_GELUBWD16 (maest_gemm) an optional fp32
  * [N] vector the column sums of the OUTPUT are accumulated into (the fc1 bias gradient: saves a maest_colsum pass).
+ * MAEST_EPI_RESID32 with out == resid (x += A W^T + b in place, blocks.N.attn.proj / mlp.fc2 of the inference encoder): the
+ * residual is not read by the SMs at all, acc + bias is added into out by the TMA engine (cp.reduce.async.bulk.tensor .add.f32,
+ * one add per element: deterministic); with out != resid the epilogue loads, adds and stores.  Both forms give
+ * resid + (acc + bias) up to the order of the two fp32 additions.  Environment MAEST_RESID_REDUCE=0 forces the second form.
  * N % 32 == 0, K % 8 == 0. */
 int32_t maest_linear_fwd(const void* a, int64_t lda, const void* w, int64_t ldw, const float* bias, int32_t M,
                          int32_t N, int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out,
@@ -165,7 +169,8 @@ int32_t maest_linear_fwd(const void* a, int64_t lda, const void* w, int64_t ldw,
  *   a_mn = 0: A is [M, K] with K contiguous;  a_mn = 1: A is stored [K, M] with M contiguous (e.g. dY for a weight gradient)
  *   b_mn = 0: B is [N, K] with K contiguous;  b_mn = 1: B is stored [K, N] with N contiguous (e.g. W for an input gradient)
  * so forward (0,0), input-gradient (0,1) and weight-gradient (1,1) GEMMs all read activations, gradients and weights in their
- * natural layouts.  aux16: MAEST_EPI_GELU16 optional 2nd output (pre-activation); MAEST_EPI_GELUBWD16 input.
+ * natural layouts.  aux16: MAEST_EPI_GELU16 optional 2nd output (pre-activation); MAEST_EPI_GELUBWD16 input (an input gradient
+ * has no bias term: bias must be NULL there, error -1 otherwise).
  * k_splits > 1 splits the reduction across CTAs (MAEST_EPI_ATOMIC32 only). */
 int32_t maest_gemm(const void* a, int64_t lda, int32_t a_mn, const void* b, int64_t ldb, int32_t b_mn, const float* bias,
                    int32_t M, int32_t N, int32_t K, int32_t op_dtype, int32_t epilogue, void* out, int64_t ld_out,

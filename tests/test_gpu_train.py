@@ -121,6 +121,14 @@ def test_attention_backward_vs_autograd(dt, BN):
         assert rel(dqkv[:, lo:hi], qd.grad[:, lo:hi]) < tol
 
 
+def test_gelubwd_rejects_bias():
+    a = torch.zeros(128, 64, dtype=torch.float16, device="cuda")
+    w = torch.zeros(64, 128, dtype=torch.float16, device="cuda")
+    pre = torch.zeros(128, 128, dtype=torch.float16, device="cuda")
+    with pytest.raises(RuntimeError, match="takes no bias"):
+        ops.gemm(a, w, _lib.EPI_GELUBWD16, 128, 128, 64, b_mn=True, aux16=pre, bias=torch.zeros(128, device="cuda"))
+
+
 def test_layernorm_bwd_mixup_bce_units():
     g = torch.Generator().manual_seed(7)
     rows = 1000
