@@ -718,6 +718,7 @@ int32_t maest_attention_bwd(const void* qkv, const void* o, const void* d_o, con
                             void* dqkv, int32_t B, int32_t N, int32_t H, int32_t op_dtype, void* stream) {
   if (B <= 0 || N <= 0) return 0;
   if (H != 12) return fail(-1, "attention_bwd: H must be 12");
+  if (reinterpret_cast<uintptr_t>(dqkv) & 31) return fail(-4, "attention_bwd: dqkv must be 32-byte aligned (256-bit stores)");
   cudaStream_t st = (cudaStream_t)stream;
   const long M = long(B) * N;
   CUtensorMap tq, td, tdq;

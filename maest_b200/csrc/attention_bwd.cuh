@@ -331,13 +331,25 @@ attention_bwd_kernel(const __grid_constant__ CUtensorMap tmap_qkv, const __grid_
           if (lane == 0) mbar_arrive(dkv_free);
         }
         if (key < p.N) {
+          // lane = key row: 256-bit stores write whole 32-byte sectors (16-byte ones left half-sector writes to L2)
           typename O16::T* d = dst + (which + 1) * p.H * 64 + c * 32;
+#ifdef ATTB_STG128
 #pragma unroll
           for (int k = 0; k < 32; k += 8)
             st_global_v4(d + k, O16::pack(__uint_as_float(v[k]), __uint_as_float(v[k + 1])),
                          O16::pack(__uint_as_float(v[k + 2]), __uint_as_float(v[k + 3])),
                          O16::pack(__uint_as_float(v[k + 4]), __uint_as_float(v[k + 5])),
                          O16::pack(__uint_as_float(v[k + 6]), __uint_as_float(v[k + 7])));
+#else
+#pragma unroll
+          for (int k = 0; k < 32; k += 16) {
+            uint32_t w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = O16::pack(__uint_as_float(v[k + 2 * j]), __uint_as_float(v[k + 2 * j + 1]));
+            asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(d + k), "r"(w[0]), "r"(w[1]), "r"(w[2]), "r"(w[3]),
+                         "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+          }
+#endif
         }
       }
     };
