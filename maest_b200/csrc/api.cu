@@ -475,6 +475,7 @@ int32_t maest_set_gemm_mode(int32_t pair_mode) {
 int32_t maest_attention_fwd(const void* qkv, void* out, float* lse, int32_t B, int32_t N, int32_t H, int32_t op_dtype,
                             int32_t variant, void* stream) {
   if (B <= 0 || N <= 0) return 0;
+  if (reinterpret_cast<uintptr_t>(out) & 31) return fail(-4, "attention_fwd: out must be 32-byte aligned (256-bit stores)");
   CUtensorMap tq;
   int r;
   if ((r = make_tmap(&tq, qkv, op_dtype, uint64_t(B) * N, uint64_t(3) * H * ATT_D, uint64_t(3) * H * ATT_D, 128))) return r;

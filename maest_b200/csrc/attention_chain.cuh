@@ -457,6 +457,7 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
 #endif
       }
       if (qrow < p.N) {
+#ifdef ATC_STG128
 #pragma unroll
         for (int i = 0; i < 32; i += 8)
           st_global_v4(dst + oh * 32 + i,
@@ -464,6 +465,18 @@ attention_fwd_chain_kernel(const __grid_constant__ CUtensorMap tmap_q, const __g
                        O16::pack(__uint_as_float(v[i + 2]) * inv_l, __uint_as_float(v[i + 3]) * inv_l),
                        O16::pack(__uint_as_float(v[i + 4]) * inv_l, __uint_as_float(v[i + 5]) * inv_l),
                        O16::pack(__uint_as_float(v[i + 6]) * inv_l, __uint_as_float(v[i + 7]) * inv_l));
+#else
+        // lane = query row: 256-bit stores write whole 32-byte sectors (the backward's dK / dV read-out gained 4.7 % from this)
+#pragma unroll
+        for (int i = 0; i < 32; i += 16) {
+          uint32_t w[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) w[j] = O16::pack(__uint_as_float(v[i + 2 * j]) * inv_l, __uint_as_float(v[i + 2 * j + 1]) * inv_l);
+          if (oh == 0 && i == 0 && !good) w[0] = 0x7fff7fffu;
+          asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst + oh * 32 + i), "r"(w[0]), "r"(w[1]), "r"(w[2]),
+                       "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7]) : "memory");
+        }
+#endif
       }
     }
   };
