@@ -68,8 +68,12 @@ struct TmapKey {
   }
 };
 struct TmapSlot { TmapKey key; CUtensorMap map; bool valid; };
-constexpr int TMAP_CACHE_SLOTS = 1024;
-thread_local TmapSlot g_tmap_cache[TMAP_CACHE_SLOTS];
+// 4-way set-associative, round-robin replacement.  (A direct-mapped table of 1024 slots thrashed whenever two of the ~60 live
+// descriptors of a forward hashed to the same slot -- about 1.8 colliding pairs per process on average, depending on where the
+// allocator happened to put the buffers: a run-to-run lottery for tests/test_gpu_parity.py::test_tensor_map_cache_serves_repeat_calls.)
+constexpr int TMAP_CACHE_SETS = 512, TMAP_CACHE_WAYS = 4;
+thread_local TmapSlot g_tmap_cache[TMAP_CACHE_SETS * TMAP_CACHE_WAYS];
+thread_local uint8_t g_tmap_next_way[TMAP_CACHE_SETS];
 uint64_t g_tmap_hits = 0, g_tmap_misses = 0;
 
 int make_tmap_uncached(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
@@ -79,15 +83,26 @@ int make_tmap(CUtensorMap* m, const void* ptr, int dt, uint64_t rows, uint64_t c
   const TmapKey key{ptr, rows, cols, ld, box_rows, dt};
   uint64_t h = reinterpret_cast<uintptr_t>(ptr) >> 4;
   h = (h ^ (h >> 17) ^ (rows * 0x9E3779B97F4A7C15ull) ^ (cols << 7) ^ (ld << 13) ^ (uint64_t(box_rows) << 29) ^ uint64_t(dt)) * 0xD6E8FEB86659FD93ull;
-  TmapSlot& slot = g_tmap_cache[(h >> 40) % TMAP_CACHE_SLOTS];
+  const int set = int((h >> 40) % TMAP_CACHE_SETS);
+  TmapSlot* ways = &g_tmap_cache[set * TMAP_CACHE_WAYS];
   static const bool enabled = [] { const char* e = getenv("MAEST_TMAP_CACHE"); return !(e && e[0] == '0'); }();   // A/B switch
-  if (enabled && slot.valid && slot.key == key) {
-    *m = slot.map;
-    ++g_tmap_hits;
-    return 0;
+  if (enabled) {
+    for (int w = 0; w < TMAP_CACHE_WAYS; ++w) {
+      if (ways[w].valid && ways[w].key == key) {
+        *m = ways[w].map;
+        ++g_tmap_hits;
+        return 0;
+      }
+    }
   }
   const int r = dt == MAEST_F32 ? make_tmap_f32(m, ptr, rows, cols, ld, box_rows) : make_tmap_uncached(m, ptr, dt, rows, cols, ld, box_rows);
-  if (r == 0) { slot.key = key; slot.map = *m; slot.valid = true; ++g_tmap_misses; }
+  if (r == 0) {
+    int w = 0;
+    while (w < TMAP_CACHE_WAYS && ways[w].valid) ++w;                      // a free way first, else round-robin
+    if (w == TMAP_CACHE_WAYS) { w = g_tmap_next_way[set]; g_tmap_next_way[set] = uint8_t((w + 1) % TMAP_CACHE_WAYS); }
+    ways[w].key = key; ways[w].map = *m; ways[w].valid = true;
+    ++g_tmap_misses;
+  }
   return r;
 }
 
