@@ -59,7 +59,7 @@ int cur_device() {
 // (128-byte inner extent), SWIZZLE_128B, out-of-bounds elements read as zero.
 // A tensor map is a pure function of (pointer, dtype, shape, stride, box): the activations live in caller-owned buffers that
 // are reused step after step and the weights never move, so the ~200 encodes per forward step collapse into lookups of a small
-// per-thread direct-mapped cache (cuTensorMapEncodeTiled costs a microsecond or two on the host -- invisible at batch 64,
+// per-thread set-associative cache (cuTensorMapEncodeTiled costs a microsecond or two on the host -- invisible at batch 64,
 // the dominant host cost of a one-clip predict_labels call).
 struct TmapKey {
   const void* ptr; uint64_t rows, cols, ld; uint32_t box_rows; int32_t dt;
